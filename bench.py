@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native volume ray march.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one frame of the hot path (ray generation, AABB test, front-to-back march with
+windowing + compositing + early-ray termination) over BASELINE.json's headline workload:
+1024^3 uint16 synthetic `mix` volume, 1920x1080, reference step
+(1024 steps across the cube), trilinear filter, camera K2 (the volume fills the frame),
+alpha scale 0.02.  Prints ONE JSON line (rank 0).
+
+value      Mrays/s, whole job, device-timed (CUDA events), inputs resident in HBM.
+e2e        same metric through the C-ABI render-to-host call: per frame the camera/uniform
+           block goes host->device and the finished RGBA32F frame comes back to pinned host
+           memory inside the timed region.
+roofline   HBM bound: algorithmic bytes (2 B x distinct voxels referenced + 16 B x pixels)
+           / average march-kernel duration, against MEASURED_PEAKS.json's copy bandwidth.
+cpu_baseline  the CPU oracle (scalar port of the reference shader) on this box's host cores,
+           on a bounded sample of rows of the SAME frame; doubles as a full-size parity check.
+
+--impl reference times the reference's own algorithm on the host cores (the reference's
+OpenGL path cannot run: no GL stack on this image) -- the oracle port, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python")]
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/sec at 1920x1080, 1024^3 uint16, 1024 steps"
+UNIT = "Mrays/s"
+TILE_ROWS = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--camera", default="K2", choices=["K0", "K1", "K2"])
+    ap.add_argument("--alpha", type=float, default=0.02)
+    ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed"])
+    ap.add_argument("--cpu-row-stride", type=int, default=64, help="cpu_baseline renders every n-th row")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
+    return ap.parse_args()
+
+
+def workload(args):
+    from volren_b200 import workloads
+    cfg = dict(workloads.CONFIGS[args.config])
+    cfg["seed"] = workloads.SEEDS[args.config]
+    cfg["window"] = (0, cfg["vmax"])
+    cfg["name"] = (f"{args.config}: {cfg['dims'][0]}x{cfg['dims'][1]}x{cfg['dims'][2]} uint{8 * cfg['bpv']} synthetic mix, "
+                   f"{cfg['image'][0]}x{cfg['image'][1]}, step_scale {cfg['step_scale']}, camera {args.camera}, "
+                   f"alpha {args.alpha}, {args.filter}")
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the march kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def cpu_march(cfg, args, host_vol, cam, row_stride, nthreads):
+    """The oracle on every row_stride-th row of the frame.  -> (Mrays/s, seconds, rows, image, counters)"""
+    from oracle import orc
+    W, H = cfg["image"]
+    p = orc.make_params(W, H, cfg["dims"], cfg["bpv"], cam, alpha_scale=args.alpha,
+                        min_val=cfg["window"][0], max_val=cfg["window"][1],
+                        filter=1 if args.filter == "trilinear" else 0, step_scale=cfg["step_scale"],
+                        row_begin=row_stride // 2, row_stride=row_stride)
+    t0 = time.perf_counter()
+    img, cnt, _ = orc.render(p, host_vol, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    rows = np.arange(row_stride // 2, H, row_stride)
+    return rows.size * W / dt / 1e6, dt, rows, img, cnt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = workload(args)
+    from volren_b200 import workloads
+    cam = workloads.camera_block(args.camera)
+    W, H = cfg["image"]
+    # input creation is not part of the timed path: use the GPU generator when there is one
+    host_vol = None
+    try:
+        import volren_b200 as vb
+        host_vol = vb.synthetic_to_host(cfg["dims"], cfg["bpv"], cfg["vmax"], cfg["seed"], True)
+    except Exception:
+        host_vol = workloads.mix_volume(cfg["dims"], cfg["vmax"], cfg["seed"], True)
+    nthreads = os.cpu_count() or 1
+    stride = max(args.cpu_row_stride // 2, 1)
+    for _ in range(args.warmup):
+        cpu_march(cfg, args, host_vol, cam, stride * 8, nthreads)        # short warm-up frames
+    times, rays = [], 0
+    for _ in range(args.steps):
+        v, dt, rows, _, _ = cpu_march(cfg, args, host_vol, cam, stride, nthreads)
+        times.append(dt); rays = rows.size * W
+    total = float(sum(times))
+    value = rays * args.steps / total / 1e6
+    sample = f"every {stride}th row of the {W}x{H} frame ({rays} rays per step), full march"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "note": "reference OpenGL path not runnable (no GL stack); "
+                   "this is the CPU port of VolumeRenderer.cs (oracle/march_oracle.c)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import volren_b200 as vb
+    from volren_b200 import dist as vdist
+    from volren_b200 import workloads
+
+    rank, world, local_rank = vdist.init_from_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = workload(args)
+    W, H = cfg["image"]
+    dims, bpv = cfg["dims"], cfg["bpv"]
+    cam = workloads.camera_block(args.camera)
+    kernel = {"auto": vb.KERNEL_AUTO, "direct": vb.KERNEL_DIRECT, "windowed": vb.KERNEL_WINDOWED}[args.kernel]
+    params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
+                               filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
+                               step_scale=cfg["step_scale"], kernel=kernel)
+
+    ctx = vb.Context(W, H, device=local_rank)
+    want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    nvox = dims[0] * dims[1] * dims[2]
+    copy = torch.empty(nvox * bpv, dtype=torch.uint8, device=dev) if want_cpu else None
+    ctx.upload_synthetic(dims, bpv, cfg["vmax"], cfg["seed"], True, copy_out_dptr=copy.data_ptr() if want_cpu else 0)
+    host_vol = None
+    if want_cpu:
+        host_vol = copy.cpu().numpy().view(np.uint8 if bpv == 1 else np.uint16)
+        del copy
+        torch.cuda.empty_cache()
+    ctx.set_camera(cam)
+    ctx.set_params(params)
+    ctx.set_partition(rank, world, TILE_ROWS)
+    rows = ctx.owned_rows()
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    local = torch.empty((rows, W, 4), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world, rows, W, 4), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    frame = torch.empty((H, W, 4), dtype=torch.float32, device=dev) if rank == 0 else None
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    kernel_ms = []
+    launches = [0]
+    used = [0]
+
+    def step():
+        if world == 1:
+            st = ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
+        else:
+            st = ctx.render_device(local.data_ptr(), compact=True, stream=sptr)
+            vdist.gather_tiles(local, gathered, dst=0)
+            if rank == 0:
+                ctx.assemble_tiles(gathered.data_ptr(), frame.data_ptr(), world, TILE_ROWS, stream=sptr)
+                launches[0] += 1
+        kernel_ms.append(st.kernel_ms)
+        launches[0] += st.kernel_launches
+        used[0] = st.kernel_used
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # algorithmic bytes (instrumentation pass, not timed)
+    counted = None
+    if not args.no_count:
+        counted = ctx.count_frame()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    kernel_ms.clear(); launches[0] = 0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    timed_launches = launches[0]
+    timed_kernel_ms = list(kernel_ms)
+
+    # e2e: through the C-ABI with host buffers, copies inside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.set_camera(cam)
+        ctx.set_params(params)
+        if world == 1:
+            ctx.render_to_host_ptr(pinned.data_ptr())
+        else:
+            step()
+            if rank == 0:
+                pinned.copy_(frame, non_blocking=True)
+                torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+
+    rays_per_frame = W * H
+    value = rays_per_frame * args.steps / (dev_ms * 1e-3) / 1e6
+    e2e_value = rays_per_frame * args.steps / (e2e_ms * 1e-3) / 1e6
+    avg_kernel_ms = float(np.mean(timed_kernel_ms))
+    peak, peak_src = measured_peak()
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel"}.get(used[0], "?"),
+            "kernel_ms_avg": avg_kernel_ms}
+    if counted is not None:
+        owned_px = sum(min(TILE_ROWS, H - t0_ * TILE_ROWS) for t0_ in range(rank, (H + TILE_ROWS - 1) // TILE_ROWS, world)) * W
+        bytes_alg = bpv * counted["distinct_voxels"] + 16 * owned_px
+        roof["achieved"] = bytes_alg / (avg_kernel_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["algorithmic_bytes_per_launch"] = bytes_alg
+        roof["distinct_voxels"] = counted["distinct_voxels"]
+        roof["samples_per_launch"] = counted["samples"]
+        roof["rays_hit"] = counted["rays_hit"]
+        roof["gsamples_per_s"] = counted["samples"] / (avg_kernel_ms * 1e-3) / 1e9
+    tr = ncu_traffic()
+    if tr and tr.get("kernel") == roof["kernel"] and tr.get("workload_key") == f"{args.config}/{args.camera}/{args.filter}/{args.alpha}":
+        roof["traffic"] = tr.get("dram_bytes_per_launch")
+
+    cpu = None
+    if want_cpu:
+        nthreads = os.cpu_count() or 1
+        v, dt, rows_idx, img_cpu, cnt = cpu_march(cfg, args, host_vol, cam, args.cpu_row_stride, nthreads)
+        ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
+        torch.cuda.synchronize()
+        img_gpu = frame.cpu().numpy()
+        err = float(np.abs(img_gpu[rows_idx].astype(np.float64) - img_cpu[rows_idx].astype(np.float64)).max())
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"every {args.cpu_row_stride}th row of the same {W}x{H} frame ({rows_idx.size * W} rays, "
+                         f"{cnt['samples']} samples, {dt:.1f} s of CPU work on {nthreads} threads)",
+               "parity_max_abs_err_on_sample": err,
+               "parity_bit_exact_on_sample": bool(np.array_equal(img_gpu[rows_idx].view(np.uint32), img_cpu[rows_idx].view(np.uint32)))}
+
+    d2h = W * H * 16
+    h2d = 84 + 4 * 10 + 1024 + 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, one gather",
+                   "l2": "inputs larger than L2 (2 GiB volume vs 126 MB L2); no flush needed",
+                   "kernel": roof["kernel"]},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": timed_launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,172 @@
+/*
+ * volren_b200.h -- C-ABI of the B200-native direct-volume raycaster (libvolren_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of gallickgunner/Volume-Renderer: what the
+ * reference does between RendererCore::readVolumeData's glTexImage3D and the RGBA32F image
+ * RendererCore::render leaves in its FBO.  The reference has no FFI; RendererCore talks to
+ * OpenGL directly.  Each entry point below names the reference GL call site it replaces
+ * (paths relative to the reference tree).  Plain C types only: no torch, no C++, no CUDA
+ * types in the signatures (a CUDA stream is passed as void*).
+ *
+ * Conventions
+ *   - every function returns VR_OK (0) or a negative vr_status; vr_last_error() returns a
+ *     human-readable message for the calling thread's last failure.  Nothing throws across
+ *     the ABI, nothing aborts.
+ *   - one caller thread per context (the reference is single threaded, RendererGUI.cpp:105).
+ *   - images are W*H*4 float32, premultiplied RGBA with r=g=b, row 0 = BOTTOM of the view
+ *     (GL image origin, VolumeRenderer.cs:58,96).
+ *   - there is NO CPU fallback: every compute entry point fails with VR_ERR_CUDA when no
+ *     CUDA device is usable.
+ */
+#ifndef VOLREN_B200_H
+#define VOLREN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VR_API __attribute__((visibility("default")))
+#else
+#define VR_API
+#endif
+
+typedef enum vr_status {
+    VR_OK = 0,
+    VR_ERR_INVALID = -1,        /* bad argument                                   */
+    VR_ERR_CUDA = -2,           /* CUDA runtime/driver error (message has detail) */
+    VR_ERR_NO_VOLUME = -3,      /* render before upload                           */
+    VR_ERR_OOM = -4,
+    VR_ERR_IO = -5,
+    VR_ERR_FORMAT = -6          /* malformed .raw.inf / .pvm                      */
+} vr_status;
+
+enum { VR_FILTER_NEAREST = 0, VR_FILTER_TRILINEAR = 1 };
+
+/* kernel selection (all produce bit-identical images) */
+enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2 };
+
+typedef struct vr_context vr_context;
+
+/* The shader's plain uniforms (VolumeRenderer.cs:39-45; set by RendererCore.cpp:56-110 via
+ * glUniform*) plus the documented extensions. */
+typedef struct vr_params {
+    float   alpha_scale;        /* location 0, RendererCore::setAlpha   RendererCore.cpp:56-60 */
+    int32_t min_val;            /* location 2, the UNIFORM value, i.e. after the +1000 rule
+                                   for 16-bit data, RendererCore.cpp:62-71                    */
+    int32_t max_val;            /* location 3, RendererCore.cpp:73-82                          */
+    int32_t is_mip;             /* location 4, RendererCore.cpp:84-88                          */
+    int32_t view_top;           /* location 5, RendererCore.cpp:95                             */
+    int32_t view_bottom;        /* location 6, RendererCore.cpp:96                             */
+    /* ---- extensions; zero-initialised struct + vr_params_default() = reference behaviour */
+    int32_t filter;             /* VR_FILTER_*; NEAREST is what an integer texture does        */
+    float   step_scale;         /* march step = reference step (VolumeRenderer.cs:109) * this  */
+    int32_t opacity_correction; /* a' = 1-(1-a)^step_scale (identity when step_scale == 1)     */
+    int32_t use_tf;             /* src.a = tf_lut[round(v*255)] instead of src.a = v           */
+    float   tf_lut[256];
+    int32_t kernel;             /* VR_KERNEL_*                                                 */
+} vr_params;
+
+typedef struct vr_render_stats {
+    float    kernel_ms;         /* CUDA-event time of the march kernel(s) only; mirrors the
+                                   GL_TIME_ELAPSED query, RendererCore.cpp:149-153             */
+    float    total_ms;          /* whole call incl. copies (host-side clock)                   */
+    uint32_t kernel_launches;   /* kernels of this library launched by the call                */
+    uint32_t kernel_used;       /* VR_KERNEL_* actually run                                    */
+} vr_render_stats;
+
+typedef struct vr_volume_stats {
+    int32_t min_value, max_value;   /* RendererCore.cpp:362-384                                */
+    float   histogram[256];         /* 0..100, RendererCore.cpp:386-405                        */
+} vr_volume_stats;
+
+/* ---- library ---- */
+VR_API const char* vr_version(void);
+VR_API const char* vr_last_error(void);
+VR_API void        vr_params_default(vr_params* p);      /* RendererCore::RendererCore, RendererCore.cpp:13-26 */
+VR_API int         vr_device_count(int* count);
+
+/* ---- context: replaces RendererCore::setup/setupFBO (RendererCore.cpp:34-44,184-219):
+ *      a W x H RGBA32F render target on CUDA device `device`. ---- */
+VR_API int  vr_create(int device, int width, int height, vr_context** out);
+VR_API void vr_destroy(vr_context* ctx);
+VR_API int  vr_resize(vr_context* ctx, int width, int height);
+VR_API int  vr_image_size(const vr_context* ctx, int* width, int* height);
+
+/* ---- volume upload: replaces glTexImage3D(GL_R8UI|GL_R16UI ...) + the CLAMP_TO_EDGE state,
+ *      RendererCore.cpp:408-419.  voxels: x fastest, then y, then z; tightly packed
+ *      (GL_UNPACK_ALIGNMENT 1, RendererCore.cpp:417-418); host byte order as is.  The caller
+ *      keeps ownership of `voxels` (the reference frees it right after, :420-433). ---- */
+VR_API int vr_upload_volume(vr_context* ctx, const void* voxels, const uint64_t dims[3],
+                            int bytes_per_voxel, const float voxel_size[3]);
+/* same, source already resident in this device's HBM */
+VR_API int vr_upload_volume_device(vr_context* ctx, const void* d_voxels, const uint64_t dims[3],
+                                   int bytes_per_voxel, const float voxel_size[3]);
+/* replaces glUniform3f(1, voxel_size...) RendererCore.cpp:103 */
+VR_API int vr_set_voxel_size(vr_context* ctx, const float voxel_size[3]);
+
+/* ---- min/max scan + 256-bin histogram on the GPU: RendererCore.cpp:360-405
+ *      (64-bit safe; the reference's skip of index 8390640 is not replicated) ---- */
+VR_API int vr_volume_stats_get(vr_context* ctx, vr_volume_stats* out);
+
+/* ---- camera block: replaces glBufferData(GL_UNIFORM_BUFFER, 84 bytes) RendererCore.cpp:
+ *      221-240; the same 21 floats Camera::setUBO emits (Camera.cpp:59-80): mat4 view_mat
+ *      column-major, vec4 eye, float view_plane_dist. ---- */
+VR_API int vr_set_camera(vr_context* ctx, const float cam21[21]);
+
+/* ---- uniforms: replaces the glUniform* calls of RendererCore.cpp:56-110 ---- */
+VR_API int vr_set_params(vr_context* ctx, const vr_params* p);
+VR_API int vr_get_params(const vr_context* ctx, vr_params* p);
+
+/* ---- multi-GPU screen-row-tile partition (no reference counterpart):
+ *      this context renders only row tiles t with t % world == rank, tile = tile_rows rows.
+ *      rank 0 / world 1 (default) renders everything. ---- */
+VR_API int vr_set_partition(vr_context* ctx, int rank, int world, int tile_rows);
+/* number of rows this context owns, and bytes of its compact (owned rows only) image */
+VR_API int vr_owned_rows(const vr_context* ctx, int* rows);
+
+/* ---- render: replaces glDispatchCompute + the timer query, RendererCore.cpp:147-155.
+ *      vr_render writes the full W*H*4 float frame to HOST memory (rows this context does
+ *      not own are zero).  vr_render_device writes into DEVICE memory on `cuda_stream`
+ *      (a cudaStream_t, may be NULL; d_rgba == NULL renders into the context's own frame,
+ *      the counterpart of the reference's FBO texture): `compact` = 0 -> full frame, rows not owned are left
+ *      untouched; `compact` = 1 -> only the owned rows, packed in tile order (what the
+ *      multi-GPU gather sends).  Both are synchronous like the reference (it blocks on the
+ *      timer query every frame, RendererCore.cpp:152). ---- */
+VR_API int vr_render(vr_context* ctx, float* host_rgba, vr_render_stats* stats);
+/* copy of the context's own frame (the image the last vr_render / vr_render_device with
+ * d_rgba == NULL left behind) to host memory; replaces glReadPixels on the FBO */
+VR_API int vr_read_frame(vr_context* ctx, float* host_rgba);
+VR_API int vr_render_device(vr_context* ctx, float* d_rgba, int compact, void* cuda_stream,
+                            vr_render_stats* stats);
+/* rank-major compact tiles [world][owned rows][W][4] -> full frame, on the device
+ * (the de-interleave after the NCCL gather) */
+VR_API int vr_assemble_tiles(vr_context* ctx, const float* d_gathered, float* d_frame,
+                             int world, int tile_rows, void* cuda_stream);
+
+/* ---- display/save step after the path: float RGBA -> RGB8 (clamp, no gamma), vertical
+ *      flip; replaces glBlitFramebuffer/glReadPixels, RendererCore.cpp:158-171 ---- */
+VR_API int vr_read_rgb8(vr_context* ctx, uint8_t* host_rgb, int flip_vertical);
+
+/* ---- instrumentation (not on the timed path): exact number of distinct voxels referenced
+ *      by the current frame and number of samples taken; feeds the roofline's algorithmic
+ *      bytes. ---- */
+VR_API int vr_count_frame(vr_context* ctx, uint64_t* distinct_voxels, uint64_t* samples,
+                          uint64_t* rays_hit);
+
+/* ---- deterministic synthetic volume `mix` generated straight into HBM and
+ *      uploaded; with d_copy_out != NULL the raw x-fastest volume is also copied there
+ *      (device pointer, dims[0]*dims[1]*dims[2]*bytes_per_voxel bytes). ---- */
+VR_API int vr_upload_synthetic(vr_context* ctx, const uint64_t dims[3], int bytes_per_voxel,
+                               const float voxel_size[3], uint32_t vmax, uint32_t seed,
+                               int with_hash_noise, void* d_copy_out);
+/* same generator into host memory through the GPU (for handing the oracle the same data) */
+VR_API int vr_synthetic_to_host(int device, const uint64_t dims[3], int bytes_per_voxel,
+                                uint32_t vmax, uint32_t seed, int with_hash_noise, void* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLREN_B200_H */

@@ -1,0 +1,153 @@
+// kernels_aux.cuh -- HBM-bound helper kernels either side of the march:
+// volume ingest (edge-replicated padding, min/max, histogram), synthetic volume generation,
+// divisor verification, tile assembly after the multi-GPU gather, RGB8 read-back, popcount.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "march_device.cuh"
+
+namespace vr {
+
+// ---- ingest: linear x-fastest volume -> edge-replicated padded volume --------------------
+// One thread per 4 padded voxels along x; grid-stride over rows.  Replaces what the GL driver
+// does inside glTexImage3D + GL_CLAMP_TO_EDGE (RendererCore.cpp:408-419).
+template <typename T>
+__global__ void pad_volume_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                  int nx, int ny, int nz, uint32_t pitch)
+{
+    const uint64_t rows = (uint64_t)(ny + 2) * (uint64_t)(nz + 2);
+    for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int jz = (int)(row / (uint64_t)(ny + 2));
+        const int jy = (int)(row - (uint64_t)jz * (uint64_t)(ny + 2));
+        const int y = min(max(jy - 1, 0), ny - 1), z = min(max(jz - 1, 0), nz - 1);
+        const T* s = src + ((uint64_t)z * ny + y) * (uint64_t)nx;
+        T* d = dst + row * (uint64_t)pitch;
+        for (uint32_t jx = threadIdx.x; jx < pitch; jx += blockDim.x) {
+            const int x = min(max((int)jx - 1, 0), nx - 1);
+            d[jx] = s[x];
+        }
+    }
+}
+
+// ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
+template <typename T>
+__global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)
+{
+    unsigned int lo = 0xffffffffu, hi = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned int v = src[i];
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
+}
+
+// ---- ingest: 256-bin histogram (RendererCore.cpp:386-398) ---------------------------------
+// 8-bit: bin = value; 16-bit: bin = round(value * 255.0f / max_dataset_val); bin 0 skipped.
+template <typename T>
+__global__ void histogram_kernel(const T* __restrict__ src, uint64_t n, float max_dataset_val,
+                                 unsigned long long* out_bins)
+{
+    __shared__ unsigned int bins[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned int v = src[i];
+        if (sizeof(T) == 2) {
+            const float scaled = roundf(fdiv(fmul((float)v, 255.0f), max_dataset_val));
+            v = (unsigned int)scaled & 0xffffu;      // assignment to uint16_t, RendererCore.cpp:394
+        }
+        if (v == 0 || v > 255) continue;
+        atomicAdd(&bins[v], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (bins[i]) atomicAdd(&out_bins[i], (unsigned long long)bins[i]);
+}
+
+// ---- synthetic volume `mix` --------------------------------------------------
+template <typename T>
+__global__ void synth_mix_kernel(T* __restrict__ dst, int nx, int ny, int nz, uint32_t vmax,
+                                 uint32_t seed, int with_hash)
+{
+    const uint64_t n = (uint64_t)nx * ny * nz;
+    const double TWO_PI = 6.283185307179586476925286766559;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)(idx % (uint64_t)nx);
+        const uint64_t t = idx / (uint64_t)nx;
+        const uint32_t j = (uint32_t)(t % (uint64_t)ny);
+        const uint32_t k = (uint32_t)(t / (uint64_t)ny);
+        const double px = ((double)i + 0.5) / (double)nx, py = ((double)j + 0.5) / (double)ny,
+                     pz = ((double)k + 0.5) / (double)nz;
+        const double ddx = px - 0.5, ddy = py - 0.5, ddz = pz - 0.5;
+        const double r = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+        const double s1 = (r - 0.30) / 0.04, s2 = (r - 0.15) / 0.03;
+        double f = 0.70 * (0.6 * exp(-(s1 * s1)) + 0.4 * exp(-(s2 * s2)))
+                 + 0.25 * (0.5 + 0.5 * sin(TWO_PI * (3.0 * px + 0.1)) * sin(TWO_PI * (2.0 * py + 0.2)) * sin(TWO_PI * (5.0 * pz + 0.3)));
+        if (with_hash) {
+            uint32_t h = (i * 73856093u) ^ (j * 19349663u) ^ (k * 83492791u) ^ seed;
+            h *= 2654435761u;
+            f += 0.05 * ((double)h / 4294967296.0);
+        }
+        f = fmin(fmax(f, 0.0), 1.0);
+        dst[idx] = (T)(uint32_t)floor((double)vmax * f + 0.5);
+    }
+}
+
+// ---- Markstein division check: all 2^23 significands against div.rn ------------------------
+__global__ void verify_divisor_kernel(float d, float inv, unsigned int* mismatch)
+{
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (1u << 23)) return;
+    const float a = __uint_as_float(0x3F800000u | m);
+    const float q = div_by<DIV_MARKSTEIN>(a, d, inv);
+    if (__float_as_uint(q) != __float_as_uint(fdiv(a, d))) atomicOr(mismatch, 1u);
+}
+
+// ---- multi-GPU: rank-major compact tiles -> full frame (after the NCCL gather) -------------
+__global__ void assemble_tiles_kernel(const float4* __restrict__ gathered, float4* __restrict__ frame,
+                                      int W, int H, int world, int tile_rows, int rows_per_rank)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const int tile = y / tile_rows, r_in = y - tile * tile_rows;
+    const int rank = tile % world, tile_local = tile / world;
+    const int local_row = tile_local * tile_rows + r_in;
+    frame[(size_t)y * W + x] = gathered[((size_t)rank * rows_per_rank + local_row) * W + x];
+}
+
+// ---- display step: RGBA32F -> RGB8, clamp, round to nearest, optional vertical flip ---------
+// (glBlitFramebuffer / glReadPixels(GL_RGB, GL_UNSIGNED_BYTE), RendererCore.cpp:158-171)
+__global__ void rgba32f_to_rgb8_kernel(const float4* __restrict__ frame, uint8_t* __restrict__ rgb,
+                                       int W, int H, int flip)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 p = frame[(size_t)y * W + x];
+    const int oy = flip ? (H - 1 - y) : y;
+    uint8_t* o = rgb + ((size_t)oy * W + x) * 3;
+    const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float v = c[i];
+        v = (v >= 0.0f) ? v : 0.0f;            // NaN -> 0
+        v = fminf(v, 1.0f);
+        o[i] = (uint8_t)__float2int_rn(fmul(v, 255.0f));
+    }
+}
+
+__global__ void popcount_kernel(const unsigned int* __restrict__ bits, uint64_t nwords, unsigned long long* out)
+{
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x)
+        acc += __popc(bits[i]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+}  // namespace vr

@@ -1,0 +1,674 @@
+// volren_abi.cu -- context management and the C-ABI of libvolren_b200.so (include/volren_b200.h).
+//
+// Host code in this file evaluates the per-frame constants (frame.h) and must be compiled
+// with -Xcompiler -ffp-contract=off.  There is no CPU fallback anywhere in this library.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "volren_b200.h"
+#include "frame.h"
+#include "march_device.cuh"
+#include "kernel_direct.cuh"
+#include "kernel_windowed.cuh"
+#include "kernels_aux.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    cudaGetLastError();   // clear sticky-less errors
+    return fail(e == cudaErrorMemoryAllocation ? VR_ERR_OOM : VR_ERR_CUDA, buf);
+}
+
+#define VR_CUDA(call)                                                   \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);           \
+    } while (0)
+
+inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct vr_context {
+    int device = 0;
+    int W = 0, H = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float* d_frame = nullptr;            // W*H*4
+    uint8_t* d_rgb8 = nullptr;           // W*H*3
+    // volume (padded, edge replicated)
+    void* d_vol = nullptr;
+    uint64_t vol_bytes = 0;
+    int32_t dim[3] = {0, 0, 0};
+    int bpv = 0;
+    uint32_t pitch = 0;                  // elements
+    uint64_t slice = 0;                  // elements
+    float voxel_size[3] = {1.f, 1.f, 1.f};
+    vr_volume_stats stats{};
+    bool have_stats = false;
+    // state
+    float cam[21];
+    bool have_cam = false;
+    vr_params params;
+    float* d_lut = nullptr;
+    int rank = 0, world = 1, tile_rows = 8;
+    // Markstein verification cache: divisor bits -> ok
+    std::map<uint32_t, bool> div_ok;
+    unsigned int* d_flag = nullptr;
+    // windowed kernel scratch
+    vr::WindowedState win;
+};
+
+namespace {
+
+int owned_rows_of(int H, int rank, int world, int tile_rows)
+{
+    const int tiles = (H + tile_rows - 1) / tile_rows;
+    int rows = 0;
+    for (int t = rank; t < tiles; t += world) {
+        const int y0 = t * tile_rows;
+        rows += std::min(tile_rows, H - y0);
+    }
+    return rows;
+}
+
+// rows of the compact image: every owned tile padded to tile_rows (keeps the gather regular)
+int compact_rows_of(int H, int rank, int world, int tile_rows)
+{
+    const int tiles = (H + tile_rows - 1) / tile_rows;
+    const int owned_tiles = (tiles - rank + world - 1) / world;
+    (void)rank;
+    return owned_tiles * tile_rows;
+}
+
+int max_compact_rows(int H, int world, int tile_rows)
+{
+    return compact_rows_of(H, 0, world, tile_rows);
+}
+
+int verify_divisor(vr_context* c, float d, bool* ok)
+{
+    uint32_t bits;
+    std::memcpy(&bits, &d, 4);
+    auto it = c->div_ok.find(bits);
+    if (it != c->div_ok.end()) { *ok = it->second; return VR_OK; }
+    if (!(d > 0.0f) || std::isinf(d)) { c->div_ok[bits] = false; *ok = false; return VR_OK; }
+    VR_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(unsigned int), c->stream));
+    vr::verify_divisor_kernel<<<(1u << 23) / 256, 256, 0, c->stream>>>(d, 1.0f / d, c->d_flag);
+    VR_CUDA(cudaGetLastError());
+    unsigned int flag = 1;
+    VR_CUDA(cudaMemcpyAsync(&flag, c->d_flag, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    c->div_ok[bits] = (flag == 0);
+    *ok = (flag == 0);
+    return VR_OK;
+}
+
+struct LaunchPlan {
+    vr::FrameConsts fc;
+    bool generic;
+    int tcdiv;
+    int local_rows;
+};
+
+int make_plan(vr_context* c, int compact, LaunchPlan* plan)
+{
+    if (!c->d_vol) return fail(VR_ERR_NO_VOLUME, "render: no volume uploaded");
+    if (!c->have_cam) return fail(VR_ERR_INVALID, "render: no camera set");
+    vr::FrameConsts& fc = plan->fc;
+    std::memset(&fc, 0, sizeof fc);
+    vr::compute_frame_consts(fc, c->W, c->H, c->dim, c->voxel_size, c->cam, c->params);
+    fc.rank = c->rank; fc.world = c->world; fc.tile_rows = c->tile_rows; fc.compact = compact;
+    plan->local_rows = compact_rows_of(c->H, c->rank, c->world, c->tile_rows);
+
+    const vr_params& p = c->params;
+    bool generic = p.is_mip == 1 || p.use_tf != 0 || p.view_top == 1 || p.view_bottom == 1 ||
+                   fc.opacity_correction || !(p.max_val > p.min_val);
+    if (!generic) {
+        bool ok = false;
+        int rc = verify_divisor(c, fc.frange, &ok);
+        if (rc != VR_OK) return rc;
+        if (!ok) generic = true;
+    }
+    int tcdiv = fc.tc_div_mode;
+    if (tcdiv == vr::DIV_MARKSTEIN) {
+        for (int i = 0; i < 3; ++i) {
+            if (vr::is_pow2_float(fc.denom[i])) continue;
+            bool ok = false;
+            int rc = verify_divisor(c, fc.denom[i], &ok);
+            if (rc != VR_OK) return rc;
+            if (!ok) tcdiv = vr::DIV_IEEE;
+        }
+    }
+    if (generic) tcdiv = vr::DIV_IEEE;
+    fc.tc_div_mode = tcdiv;
+    plan->generic = generic;
+    plan->tcdiv = tcdiv;
+    return VR_OK;
+}
+
+template <typename T, bool COUNT>
+int launch_direct_t(vr_context* c, const LaunchPlan& plan, const vr::DirectArgs& args, cudaStream_t s)
+{
+    using namespace vr;
+    const dim3 block(DIRECT_BLOCK_W * DIRECT_BLOCK_H);
+    const dim3 grid((c->W + DIRECT_BLOCK_W - 1) / DIRECT_BLOCK_W,
+                    (plan.local_rows + DIRECT_BLOCK_H - 1) / DIRECT_BLOCK_H);
+    const FrameConsts& fc = plan.fc;
+    if (COUNT || plan.generic) {
+        march_direct_kernel<T, VR_FILTER_NEAREST, DIV_IEEE, true, COUNT><<<grid, block, 0, s>>>(fc, args);
+    } else if (fc.filter == VR_FILTER_NEAREST) {
+        switch (plan.tcdiv) {
+            case DIV_RECIP_EXACT: march_direct_kernel<T, VR_FILTER_NEAREST, DIV_RECIP_EXACT, false, false><<<grid, block, 0, s>>>(fc, args); break;
+            case DIV_MARKSTEIN:   march_direct_kernel<T, VR_FILTER_NEAREST, DIV_MARKSTEIN, false, false><<<grid, block, 0, s>>>(fc, args); break;
+            default:              march_direct_kernel<T, VR_FILTER_NEAREST, DIV_IEEE, false, false><<<grid, block, 0, s>>>(fc, args); break;
+        }
+    } else {
+        switch (plan.tcdiv) {
+            case DIV_RECIP_EXACT: march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, false, false><<<grid, block, 0, s>>>(fc, args); break;
+            case DIV_MARKSTEIN:   march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_MARKSTEIN, false, false><<<grid, block, 0, s>>>(fc, args); break;
+            default:              march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_IEEE, false, false><<<grid, block, 0, s>>>(fc, args); break;
+        }
+    }
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+int launch_direct(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s)
+{
+    vr::DirectArgs args{};
+    args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
+    args.tf_lut = c->d_lut; args.out = d_out; args.local_rows = plan.local_rows;
+    return c->bpv == 1 ? launch_direct_t<uint8_t, false>(c, plan, args, s)
+                       : launch_direct_t<uint16_t, false>(c, plan, args, s);
+}
+
+// the march: returns which kernel ran
+int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, uint32_t* used,
+                 uint32_t* launches)
+{
+    int want = c->params.kernel;
+    const bool windowed_ok = !plan.generic && vr::windowed_supported(plan.fc, c->bpv);
+    if (want == VR_KERNEL_AUTO) want = windowed_ok ? VR_KERNEL_WINDOWED : VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_WINDOWED) {
+        int rc = vr::launch_windowed(c->win, plan.fc, c->d_vol, c->bpv, c->pitch, c->slice, d_out,
+                                     plan.local_rows, c->sm_count, s, launches);
+        if (rc != 0) return cuda_fail(cudaGetLastError(), vr::windowed_last_error());
+        *used = VR_KERNEL_WINDOWED;
+        return VR_OK;
+    }
+    *used = VR_KERNEL_DIRECT;
+    *launches = 1;
+    return launch_direct(c, plan, d_out, s);
+}
+
+int render_common(vr_context* c, float* d_out, int compact, cudaStream_t s, vr_render_stats* stats)
+{
+    LaunchPlan plan;
+    int rc = make_plan(c, compact, &plan);
+    if (rc != VR_OK) return rc;
+    uint32_t used = 0, launches = 0;
+    VR_CUDA(cudaEventRecord(c->ev0, s));
+    rc = launch_march(c, plan, d_out, s, &used, &launches);
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaEventRecord(c->ev1, s));
+    VR_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (stats) { stats->kernel_ms = ms; stats->kernel_launches = launches; stats->kernel_used = used; }
+    return VR_OK;
+}
+
+template <typename T>
+int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
+{
+    const int nx = (int)dims[0], ny = (int)dims[1], nz = (int)dims[2];
+    const uint64_t n = (uint64_t)nx * ny * nz;
+    // stats first (RendererCore.cpp:360-405)
+    unsigned int* d_mm = nullptr;
+    unsigned long long* d_bins = nullptr;
+    VR_CUDA(cudaMalloc(&d_mm, 2 * sizeof(unsigned int)));
+    VR_CUDA(cudaMalloc(&d_bins, 256 * sizeof(unsigned long long)));
+    const unsigned int init[2] = {0xffffffffu, 0u};
+    VR_CUDA(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    VR_CUDA(cudaMemsetAsync(d_bins, 0, 256 * sizeof(unsigned long long), c->stream));
+    const int blocks = c->sm_count * 8;
+    unsigned int mm[2] = {0, 255};
+    if (sizeof(T) == 2) {
+        vr::minmax_kernel<T><<<blocks, 256, 0, c->stream>>>(d_src, n, d_mm, d_mm + 1);
+        VR_CUDA(cudaGetLastError());
+        VR_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
+        VR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    vr::histogram_kernel<T><<<blocks, 256, 0, c->stream>>>(d_src, n, (float)(int)mm[1], d_bins);
+    VR_CUDA(cudaGetLastError());
+    unsigned long long bins[256];
+    VR_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof bins, cudaMemcpyDeviceToHost, c->stream));
+
+    // padded copy
+    const uint32_t pitch = (uint32_t)(round_up((uint64_t)(nx + 2) * sizeof(T), 16) / sizeof(T));
+    const uint64_t slice = (uint64_t)pitch * (uint64_t)(ny + 2);
+    const uint64_t bytes = slice * (uint64_t)(nz + 2) * sizeof(T) + 256;
+    void* d_new = nullptr;
+    cudaError_t e = cudaMalloc(&d_new, bytes);
+    if (e != cudaSuccess) { cudaFree(d_mm); cudaFree(d_bins); return cuda_fail(e, "cudaMalloc(padded volume)"); }
+    VR_CUDA(cudaMemsetAsync(d_new, 0, bytes, c->stream));
+    vr::pad_volume_kernel<T><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, (T*)d_new, nx, ny, nz, pitch);
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_mm); cudaFree(d_bins);
+
+    if (c->d_vol) cudaFree(c->d_vol);
+    c->d_vol = d_new; c->vol_bytes = bytes;
+    c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
+    c->bpv = (int)sizeof(T); c->pitch = pitch; c->slice = slice;
+    vr::windowed_invalidate(c->win);
+
+    // histogram normalisation exactly as RendererCore.cpp:361,386-405: float bins that are
+    // incremented one by one saturate at 2^24; max_value starts at the 16-bit dataset max
+    // (or -1 for 8-bit data) and is then raised by the bin counts.
+    vr_volume_stats& st = c->stats;
+    if (sizeof(T) == 2) { st.min_value = (int)mm[0]; st.max_value = (int)mm[1]; }
+    else { st.min_value = 0; st.max_value = 255; }
+    int max_value = sizeof(T) == 2 ? (int)mm[1] : -1;
+    float hist[256];
+    for (int i = 0; i < 256; ++i) {
+        const unsigned long long cnt = bins[i] > 16777216ull ? 16777216ull : bins[i];
+        hist[i] = (float)cnt;
+        if (i > 0 && hist[i] > (float)max_value) max_value = (int)hist[i];
+    }
+    for (int i = 0; i < 256; ++i) st.histogram[i] = hist[i] * 100.0f / (float)max_value;
+    c->have_stats = true;
+    return VR_OK;
+}
+
+int check_dims(const uint64_t dims[3], int bpv, const float voxel_size[3])
+{
+    if (!dims || !voxel_size) return fail(VR_ERR_INVALID, "upload: null argument");
+    if (bpv != 1 && bpv != 2) return fail(VR_ERR_INVALID, "upload: bytes_per_voxel must be 1 or 2");
+    for (int i = 0; i < 3; ++i) {
+        if (dims[i] < 1 || dims[i] > 16384) return fail(VR_ERR_INVALID, "upload: each dimension must be in [1,16384]");
+        if (!(voxel_size[i] > 0.0f) || !std::isfinite(voxel_size[i])) return fail(VR_ERR_INVALID, "upload: voxel_size must be finite and > 0");
+    }
+    return VR_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ ABI
+
+extern "C" {
+
+const char* vr_version(void) { return "volren_b200 0.1 (sm_100a)"; }
+const char* vr_last_error(void) { return g_last_error.c_str(); }
+
+void vr_params_default(vr_params* p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->alpha_scale = 1.0f;          // RendererCore.cpp:18
+    p->min_val = 0; p->max_val = 0; // RendererCore.cpp:19-20
+    p->filter = VR_FILTER_NEAREST;
+    p->step_scale = 1.0f;
+    p->kernel = VR_KERNEL_AUTO;
+}
+
+int vr_device_count(int* count)
+{
+    if (!count) return fail(VR_ERR_INVALID, "vr_device_count: null");
+    VR_CUDA(cudaGetDeviceCount(count));
+    return VR_OK;
+}
+
+int vr_create(int device, int width, int height, vr_context** out)
+{
+    if (!out) return fail(VR_ERR_INVALID, "vr_create: null out");
+    *out = nullptr;
+    if (width < 1 || height < 1 || width > 32768 || height > 32768)
+        return fail(VR_ERR_INVALID, "vr_create: image size out of range");
+    int n = 0;
+    VR_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(VR_ERR_INVALID, "vr_create: no such CUDA device");
+    VR_CUDA(cudaSetDevice(device));
+    vr_context* c = new (std::nothrow) vr_context();
+    if (!c) return fail(VR_ERR_OOM, "vr_create: out of host memory");
+    c->device = device; c->W = width; c->H = height;
+    vr_params_default(&c->params);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_frame, (size_t)width * height * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, 256 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_flag, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_lut, 0, 256 * sizeof(float));
+    if (e != cudaSuccess) { int rc = cuda_fail(e, "vr_create"); vr_destroy(c); return rc; }
+    *out = c;
+    return VR_OK;
+}
+
+void vr_destroy(vr_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    vr::windowed_release(c->win);
+    if (c->d_vol) cudaFree(c->d_vol);
+    if (c->d_frame) cudaFree(c->d_frame);
+    if (c->d_rgb8) cudaFree(c->d_rgb8);
+    if (c->d_lut) cudaFree(c->d_lut);
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int vr_resize(vr_context* c, int width, int height)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_resize: null context");
+    if (width < 1 || height < 1 || width > 32768 || height > 32768)
+        return fail(VR_ERR_INVALID, "vr_resize: image size out of range");
+    VR_CUDA(cudaSetDevice(c->device));
+    float* d_new = nullptr;
+    VR_CUDA(cudaMalloc(&d_new, (size_t)width * height * 4 * sizeof(float)));
+    cudaFree(c->d_frame);
+    if (c->d_rgb8) { cudaFree(c->d_rgb8); c->d_rgb8 = nullptr; }
+    c->d_frame = d_new; c->W = width; c->H = height;
+    return VR_OK;
+}
+
+int vr_image_size(const vr_context* c, int* width, int* height)
+{
+    if (!c || !width || !height) return fail(VR_ERR_INVALID, "vr_image_size: null");
+    *width = c->W; *height = c->H;
+    return VR_OK;
+}
+
+int vr_upload_volume(vr_context* c, const void* voxels, const uint64_t dims[3], int bpv, const float voxel_size[3])
+{
+    if (!c || !voxels) return fail(VR_ERR_INVALID, "vr_upload_volume: null argument");
+    int rc = check_dims(dims, bpv, voxel_size);
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaSetDevice(c->device));
+    const uint64_t bytes = dims[0] * dims[1] * dims[2] * (uint64_t)bpv;
+    void* d_src = nullptr;
+    VR_CUDA(cudaMalloc(&d_src, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_src, voxels, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { cudaFree(d_src); return cuda_fail(e, "vr_upload_volume: H2D copy"); }
+    rc = bpv == 1 ? ingest_from_device<uint8_t>(c, (const uint8_t*)d_src, dims)
+                  : ingest_from_device<uint16_t>(c, (const uint16_t*)d_src, dims);
+    cudaFree(d_src);
+    if (rc != VR_OK) return rc;
+    for (int i = 0; i < 3; ++i) c->voxel_size[i] = voxel_size[i];
+    return VR_OK;
+}
+
+int vr_upload_volume_device(vr_context* c, const void* d_voxels, const uint64_t dims[3], int bpv, const float voxel_size[3])
+{
+    if (!c || !d_voxels) return fail(VR_ERR_INVALID, "vr_upload_volume_device: null argument");
+    int rc = check_dims(dims, bpv, voxel_size);
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaSetDevice(c->device));
+    VR_CUDA(cudaDeviceSynchronize());   // the source may have been produced on another stream
+    rc = bpv == 1 ? ingest_from_device<uint8_t>(c, (const uint8_t*)d_voxels, dims)
+                  : ingest_from_device<uint16_t>(c, (const uint16_t*)d_voxels, dims);
+    if (rc != VR_OK) return rc;
+    for (int i = 0; i < 3; ++i) c->voxel_size[i] = voxel_size[i];
+    return VR_OK;
+}
+
+int vr_set_voxel_size(vr_context* c, const float voxel_size[3])
+{
+    if (!c || !voxel_size) return fail(VR_ERR_INVALID, "vr_set_voxel_size: null");
+    for (int i = 0; i < 3; ++i)
+        if (!(voxel_size[i] > 0.0f) || !std::isfinite(voxel_size[i]))
+            return fail(VR_ERR_INVALID, "vr_set_voxel_size: must be finite and > 0");
+    for (int i = 0; i < 3; ++i) c->voxel_size[i] = voxel_size[i];
+    return VR_OK;
+}
+
+int vr_volume_stats_get(vr_context* c, vr_volume_stats* out)
+{
+    if (!c || !out) return fail(VR_ERR_INVALID, "vr_volume_stats_get: null");
+    if (!c->have_stats) return fail(VR_ERR_NO_VOLUME, "vr_volume_stats_get: no volume uploaded");
+    *out = c->stats;
+    return VR_OK;
+}
+
+int vr_set_camera(vr_context* c, const float cam21[21])
+{
+    if (!c || !cam21) return fail(VR_ERR_INVALID, "vr_set_camera: null");
+    for (int i = 0; i < 21; ++i)
+        if (!std::isfinite(cam21[i])) return fail(VR_ERR_INVALID, "vr_set_camera: non-finite camera block");
+    std::memcpy(c->cam, cam21, sizeof(float) * 21);
+    c->have_cam = true;
+    return VR_OK;
+}
+
+int vr_set_params(vr_context* c, const vr_params* p)
+{
+    if (!c || !p) return fail(VR_ERR_INVALID, "vr_set_params: null");
+    if (p->filter != VR_FILTER_NEAREST && p->filter != VR_FILTER_TRILINEAR)
+        return fail(VR_ERR_INVALID, "vr_set_params: unknown filter");
+    if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
+    if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
+        return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_WINDOWED)
+        return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
+    if (p->use_tf) {
+        VR_CUDA(cudaSetDevice(c->device));
+        VR_CUDA(cudaMemcpyAsync(c->d_lut, p->tf_lut, 256 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        VR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->params = *p;
+    return VR_OK;
+}
+
+int vr_get_params(const vr_context* c, vr_params* p)
+{
+    if (!c || !p) return fail(VR_ERR_INVALID, "vr_get_params: null");
+    *p = c->params;
+    return VR_OK;
+}
+
+int vr_set_partition(vr_context* c, int rank, int world, int tile_rows)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_set_partition: null context");
+    if (world < 1 || rank < 0 || rank >= world || tile_rows < 1)
+        return fail(VR_ERR_INVALID, "vr_set_partition: need 0 <= rank < world and tile_rows >= 1");
+    c->rank = rank; c->world = world; c->tile_rows = tile_rows;
+    return VR_OK;
+}
+
+int vr_owned_rows(const vr_context* c, int* rows)
+{
+    if (!c || !rows) return fail(VR_ERR_INVALID, "vr_owned_rows: null");
+    *rows = max_compact_rows(c->H, c->world, c->tile_rows);
+    return VR_OK;
+}
+
+int vr_render_device(vr_context* c, float* d_rgba, int compact, void* cuda_stream, vr_render_stats* stats)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_render_device: null context");
+    if (!d_rgba) { d_rgba = c->d_frame; compact = 0; }
+    VR_CUDA(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    int rc = render_common(c, d_rgba, compact ? 1 : 0, s, stats);
+    if (rc != VR_OK) return rc;
+    if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
+int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
+{
+    if (!c || !host_rgba) return fail(VR_ERR_INVALID, "vr_render: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t bytes = (size_t)c->W * c->H * 4 * sizeof(float);
+    if (c->world > 1) VR_CUDA(cudaMemsetAsync(c->d_frame, 0, bytes, c->stream));
+    int rc = render_common(c, c->d_frame, 0, c->stream, stats);
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaMemcpyAsync(host_rgba, c->d_frame, bytes, cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
+int vr_read_frame(vr_context* c, float* host_rgba)
+{
+    if (!c || !host_rgba) return fail(VR_ERR_INVALID, "vr_read_frame: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    VR_CUDA(cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->W * c->H * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    return VR_OK;
+}
+
+int vr_assemble_tiles(vr_context* c, const float* d_gathered, float* d_frame, int world, int tile_rows, void* cuda_stream)
+{
+    if (!c || !d_gathered || !d_frame || world < 1 || tile_rows < 1)
+        return fail(VR_ERR_INVALID, "vr_assemble_tiles: bad argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const int rows_per_rank = max_compact_rows(c->H, world, tile_rows);
+    const dim3 block(128), grid((c->W + 127) / 128, c->H);
+    vr::assemble_tiles_kernel<<<grid, block, 0, s>>>((const float4*)d_gathered, (float4*)d_frame,
+                                                     c->W, c->H, world, tile_rows, rows_per_rank);
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaStreamSynchronize(s));
+    return VR_OK;
+}
+
+int vr_read_rgb8(vr_context* c, uint8_t* host_rgb, int flip_vertical)
+{
+    if (!c || !host_rgb) return fail(VR_ERR_INVALID, "vr_read_rgb8: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->W * c->H * 3;
+    if (!c->d_rgb8) VR_CUDA(cudaMalloc(&c->d_rgb8, bytes));
+    const dim3 block(128), grid((c->W + 127) / 128, c->H);
+    vr::rgba32f_to_rgb8_kernel<<<grid, block, 0, c->stream>>>((const float4*)c->d_frame, c->d_rgb8, c->W, c->H, flip_vertical ? 1 : 0);
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaMemcpyAsync(host_rgb, c->d_rgb8, bytes, cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    return VR_OK;
+}
+
+int vr_count_frame(vr_context* c, uint64_t* distinct_voxels, uint64_t* samples, uint64_t* rays_hit)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_count_frame: null context");
+    VR_CUDA(cudaSetDevice(c->device));
+    LaunchPlan plan;
+    int rc = make_plan(c, 0, &plan);
+    if (rc != VR_OK) return rc;
+    const uint64_t nvox = (uint64_t)c->dim[0] * c->dim[1] * c->dim[2];
+    const uint64_t nwords = (nvox + 31) / 32;
+    unsigned int* d_bits = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    VR_CUDA(cudaMalloc(&d_bits, nwords * sizeof(unsigned int)));
+    cudaError_t e = cudaMalloc(&d_cnt, 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(d_bits); return cuda_fail(e, "vr_count_frame: cudaMalloc"); }
+    cudaMemsetAsync(d_bits, 0, nwords * sizeof(unsigned int), c->stream);
+    cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), c->stream);
+    vr::DirectArgs args{};
+    args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
+    args.tf_lut = c->d_lut; args.out = c->d_frame; args.local_rows = plan.local_rows;
+    args.touch_bits = d_bits; args.counters = d_cnt;
+    rc = c->bpv == 1 ? launch_direct_t<uint8_t, true>(c, plan, args, c->stream)
+                     : launch_direct_t<uint16_t, true>(c, plan, args, c->stream);
+    if (rc == VR_OK) {
+        vr::popcount_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_bits, nwords, d_cnt + 2);
+        unsigned long long h[3] = {0, 0, 0};
+        e = cudaMemcpyAsync(h, d_cnt, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vr_count_frame");
+        if (samples) *samples = h[0];
+        if (rays_hit) *rays_hit = h[1];
+        if (distinct_voxels) *distinct_voxels = h[2];
+    }
+    cudaFree(d_bits); cudaFree(d_cnt);
+    return rc;
+}
+
+static int synth_into(int sm_count, cudaStream_t s, void* d_dst, const uint64_t dims[3], int bpv,
+                      uint32_t vmax, uint32_t seed, int with_hash)
+{
+    const int blocks = sm_count * 16;
+    if (bpv == 1)
+        vr::synth_mix_kernel<uint8_t><<<blocks, 256, 0, s>>>((uint8_t*)d_dst, (int)dims[0], (int)dims[1], (int)dims[2], vmax, seed, with_hash);
+    else
+        vr::synth_mix_kernel<uint16_t><<<blocks, 256, 0, s>>>((uint16_t*)d_dst, (int)dims[0], (int)dims[1], (int)dims[2], vmax, seed, with_hash);
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+int vr_upload_synthetic(vr_context* c, const uint64_t dims[3], int bpv, const float voxel_size[3],
+                        uint32_t vmax, uint32_t seed, int with_hash_noise, void* d_copy_out)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_upload_synthetic: null context");
+    int rc = check_dims(dims, bpv, voxel_size);
+    if (rc != VR_OK) return rc;
+    if (vmax > (bpv == 1 ? 255u : 65535u)) return fail(VR_ERR_INVALID, "vr_upload_synthetic: vmax too large");
+    VR_CUDA(cudaSetDevice(c->device));
+    const uint64_t bytes = dims[0] * dims[1] * dims[2] * (uint64_t)bpv;
+    void* d_src = nullptr;
+    VR_CUDA(cudaMalloc(&d_src, bytes));
+    rc = synth_into(c->sm_count, c->stream, d_src, dims, bpv, vmax, seed, with_hash_noise);
+    if (rc == VR_OK)
+        rc = bpv == 1 ? ingest_from_device<uint8_t>(c, (const uint8_t*)d_src, dims)
+                      : ingest_from_device<uint16_t>(c, (const uint16_t*)d_src, dims);
+    if (rc == VR_OK && d_copy_out) {
+        cudaError_t e = cudaMemcpy(d_copy_out, d_src, bytes, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vr_upload_synthetic: copy out");
+    }
+    cudaFree(d_src);
+    if (rc != VR_OK) return rc;
+    for (int i = 0; i < 3; ++i) c->voxel_size[i] = voxel_size[i];
+    return VR_OK;
+}
+
+int vr_synthetic_to_host(int device, const uint64_t dims[3], int bpv, uint32_t vmax, uint32_t seed,
+                         int with_hash_noise, void* host_out)
+{
+    if (!host_out) return fail(VR_ERR_INVALID, "vr_synthetic_to_host: null");
+    const float one[3] = {1.f, 1.f, 1.f};
+    int rc = check_dims(dims, bpv, one);
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VR_CUDA(cudaGetDeviceProperties(&prop, device));
+    const uint64_t bytes = dims[0] * dims[1] * dims[2] * (uint64_t)bpv;
+    void* d = nullptr;
+    VR_CUDA(cudaMalloc(&d, bytes));
+    rc = synth_into(prop.multiProcessorCount, nullptr, d, dims, bpv, vmax, seed, with_hash_noise);
+    if (rc == VR_OK) {
+        cudaError_t e = cudaMemcpy(host_out, d, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vr_synthetic_to_host: D2H");
+    }
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, screen-row tiles interleaved across
+ranks (tile t belongs to rank t % world), replicated volume, ONE gather of the finished RGBA
+tiles to rank 0 per frame over torch.distributed (NCCL on GPUs, gloo in the CPU tests),
+followed by the tile de-interleave.  No other collective touches the data path."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(backend: str = None):
+    rank, world, local_rank = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def compact_rows(height: int, world: int, tile_rows: int) -> int:
+    """Rows of every rank's compact tile buffer (rank 0's tile count, padded to whole tiles)."""
+    tiles = (height + tile_rows - 1) // tile_rows
+    return ((tiles + world - 1) // world) * tile_rows
+
+
+def owner_of_row(y: int, world: int, tile_rows: int) -> int:
+    return (y // tile_rows) % world
+
+
+def local_row_of(y: int, world: int, tile_rows: int) -> int:
+    tile = y // tile_rows
+    return (tile // world) * tile_rows + (y % tile_rows)
+
+
+def gather_tiles(local_compact: torch.Tensor, gathered: torch.Tensor | None, dst: int = 0):
+    """local_compact [rows, W, 4] on every rank -> gathered [world, rows, W, 4] on rank dst."""
+    world = dist.get_world_size()
+    if dist.get_rank() == dst:
+        assert gathered is not None and gathered.shape[0] == world
+        dist.gather(local_compact, list(gathered.unbind(0)), dst=dst)
+    else:
+        dist.gather(local_compact, None, dst=dst)
+
+
+def assemble_reference(gathered: torch.Tensor, height: int, tile_rows: int) -> torch.Tensor:
+    """Pure-torch statement of vr_assemble_tiles (used on CPU tensors by the gloo tests and as
+    the checker of the CUDA de-interleave kernel)."""
+    world, rows, W, _ = gathered.shape
+    ys = torch.arange(height)
+    tile = ys // tile_rows
+    rank = tile % world
+    local = (tile // world) * tile_rows + (ys % tile_rows)
+    return gathered[rank, local]
