@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--alpha", type=float, default=0.02)
     ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed"])
-    ap.add_argument("--cpu-row-stride", type=int, default=64, help="cpu_baseline renders every n-th row")
+    ap.add_argument("--cpu-row-stride", type=int, default=4, help="cpu_baseline renders every n-th row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
     return ap.parse_args()
@@ -168,7 +168,7 @@ def run_reference(args):
     except Exception:
         host_vol = workloads.mix_volume(cfg["dims"], cfg["vmax"], cfg["seed"], True)
     nthreads = os.cpu_count() or 1
-    stride = max(args.cpu_row_stride // 2, 1)
+    stride = max(args.cpu_row_stride * 4, 1)
     for _ in range(args.warmup):
         cpu_march(cfg, args, host_vol, cam, stride * 8, nthreads)        # short warm-up frames
     times, rays = [], 0

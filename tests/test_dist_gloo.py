@@ -1,0 +1,81 @@
+"""CPU, world_size 2 and 3 over gloo: the multi-GPU host logic -- interleaved
+row-tile ownership, the compact per-rank tile buffers, the single gather to rank 0 and the
+de-interleave.  The per-rank "render" here is the CPU oracle restricted to the rank's rows
+(the product march has no CPU path); what is under test is the partition/gather/assemble
+plumbing of volren_b200.dist, which the GPU path shares."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tile_rows, H, W, out_path):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from volren_b200 import dist as vdist
+    from oracle import orc
+    import scenarios
+    r, w, _ = vdist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    kw = dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)
+    rows = vdist.compact_rows(H, world, tile_rows)
+    local = torch.full((rows, W, 4), float("nan"), dtype=torch.float32)
+    # this rank's rows, one oracle call per owned tile
+    tiles = (H + tile_rows - 1) // tile_rows
+    for t in range(rank, tiles, world):
+        y0, y1 = t * tile_rows, min((t + 1) * tile_rows, H)
+        p = orc.make_params(W, H, dims, bpv, cam, row_begin=y0, row_end=y1, row_stride=1, **kw)
+        img, _, _ = orc.render(p, vox, nthreads=1)
+        for y in range(y0, y1):
+            assert vdist.owner_of_row(y, world, tile_rows) == rank
+            local[vdist.local_row_of(y, world, tile_rows)] = torch.from_numpy(img[y])
+    gathered = torch.empty((world, rows, W, 4), dtype=torch.float32) if rank == 0 else None
+    vdist.gather_tiles(local, gathered, dst=0)
+    if rank == 0:
+        frame = vdist.assemble_reference(gathered, H, tile_rows)
+        full, _, _ = orc.render(orc.make_params(W, H, dims, bpv, cam, **kw), vox, nthreads=2)
+        ok = np.array_equal(frame.numpy().view(np.uint32), full.view(np.uint32))
+        np.save(out_path, np.array([1 if ok else 0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,tile_rows,H", [(2, 8, 70), (2, 1, 33), (3, 4, 50)])
+def test_gather_and_assemble_equals_single_process(tmp_path, world, tile_rows, H):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker, args=(world, _free_port(), tile_rows, H, 96, out), nprocs=world, join=True)
+    assert np.load(out)[0] == 1
+
+
+def test_partition_maps_are_a_bijection():
+    from volren_b200 import dist as vdist
+    for world in (1, 2, 3, 4, 8):
+        for tile_rows in (1, 4, 8, 16):
+            for H in (1, 7, 64, 1080, 2160):
+                rows = vdist.compact_rows(H, world, tile_rows)
+                seen = set()
+                for y in range(H):
+                    r, l = vdist.owner_of_row(y, world, tile_rows), vdist.local_row_of(y, world, tile_rows)
+                    assert 0 <= r < world and 0 <= l < rows
+                    seen.add((r, l))
+                assert len(seen) == H
+                # balance: no rank owns more than one tile more than another
+                counts = [sum(1 for y in range(0, H, 1) if vdist.owner_of_row(y, world, tile_rows) == r) for r in range(world)]
+                assert max(counts) - min(counts) <= tile_rows

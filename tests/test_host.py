@@ -1,0 +1,197 @@
+"""CPU: the C++ host mirror of the reference surface (volume-renderer_b200/host/): Camera,
+CubicSpline, .raw.inf sidecar, image writers -- against hand-derived known answers
+ and, bit for bit, against the oracle restatements."""
+import math
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from volren_b200 import host
+
+DEFAULT_KNOTS = [(0, 0.0), (141, 0.759), (149, 0.45), (255, 1.0)]
+
+
+# ------------------------------------------------------------------ Camera
+
+def test_reset_camera_ubo_known_answer():
+    cam = host.Camera(30.0)
+    # Camera.cpp:34-38,56,59-80,19: [side|up|-look|eye], eye xyz1, 1/tan(15 deg)
+    exp = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 3, 1, 0, 0, 3, 1, 3.7320508]
+    assert cam.ubo() == pytest.approx(exp, abs=1e-6)
+    assert cam.ubo()[20] == pytest.approx(1.0 / math.tan(math.radians(15.0)), rel=3e-7)
+
+
+def test_zoom_moves_eye_along_look_at_in_unit_steps():
+    cam = host.Camera(30.0)
+    cam.setOrientation(1, 0, 0)        # scroll up: eye += look_at
+    u = cam.ubo()
+    assert u[16:19] == pytest.approx([0, 0, 2]) and u[12:15] == pytest.approx([0, 0, 2])
+    cam.setOrientation(-1, 0, 0)
+    cam.setOrientation(-1, 0, 0)
+    assert cam.ubo()[16:19] == pytest.approx([0, 0, 4])
+
+
+def test_orbit_matches_spherical_formulas():
+    cam = host.Camera(30.0)
+    dz, da = -0.3, 0.5
+    cam.setOrientation(0, dz, da)      # rotation speed 0.7 (Camera.h:14)
+    zen = np.float32(np.float32(np.pi) / 2) + np.float32(dz) * np.float32(0.7)
+    az = np.float32(da) * np.float32(0.7)
+    eye = 3 * np.array([math.sin(zen) * math.sin(az), math.cos(zen), math.sin(zen) * math.cos(az)])
+    u = cam.ubo()
+    assert u[16:19] == pytest.approx(eye, abs=1e-5)
+    side, up, back = u[0:3], u[4:7], u[8:11]
+    assert np.dot(side, up) == pytest.approx(0, abs=1e-6) and np.linalg.norm(side) == pytest.approx(1, abs=1e-6)
+    assert back == pytest.approx(eye / 3, abs=1e-6)          # third column is -look_at = eye/|eye|
+    assert side[1] == 0                                       # side stays horizontal
+
+
+def test_azimuth_wrap_quirk_and_zenith_clamp():
+    cam = host.Camera(30.0)
+    o = orc.OracleCamera(30.0)
+    for c in (cam, o):
+        (c.setOrientation if c is cam else c.set_orientation)(0, 0.0, -0.1)     # negative azimuth -> 2*pi - a (sic)
+    assert np.array_equal(cam.ubo().view(np.uint32), o.ubo().view(np.uint32))
+    az = np.float32(2 * np.float32(np.pi)) - np.float32(np.float32(-0.1) * np.float32(0.7))
+    assert cam.ubo()[16] == pytest.approx(3 * math.sin(az), abs=1e-5)
+    for _ in range(40):
+        cam.setOrientation(0, -0.2, 0.0)                    # zenith clamps at 0 -> pole branch
+        o.set_orientation(0, -0.2, 0.0)
+    assert cam.ubo()[17] == pytest.approx(3.0)
+    assert np.array_equal(cam.ubo().view(np.uint32), o.ubo().view(np.uint32))
+
+
+def test_camera_bitwise_equals_oracle_over_random_walk():
+    rng = np.random.default_rng(1)
+    cam, o = host.Camera(30.0), orc.OracleCamera(30.0)
+    for i in range(500):
+        r = rng.random()
+        if r < 0.15:
+            z, a, b = (1 if rng.random() < 0.5 else -1), 0.0, 0.0
+        elif r < 0.2:
+            cam.resetCamera(); o.reset(); continue
+        else:
+            z, a, b = 0, float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-0.4, 0.4))
+        cam.setOrientation(z, a, b); o.set_orientation(z, a, b)
+        a, b = cam.ubo(), o.ubo()
+        # zooming the eye onto the origin yields NaNs in the reference too (normalize(0)); the
+        # sign of a NaN is not part of the contract
+        assert (((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()), i
+
+
+def test_is_changed_is_never_cleared_like_the_reference():
+    cam = host.Camera(30.0)
+    assert cam.is_changed
+    cam.ubo()
+    assert cam.is_changed          # Camera.cpp:63-72 returns before :79
+
+
+# ------------------------------------------------------------------ CubicSpline
+
+def test_default_knots_known_answers():
+    """SURVEY.md 8c, fp32 evaluation of CubicSpline.cpp:50-115 on AlphaControlSplineWidget.cpp:56-59."""
+    s = host.CubicSpline(DEFAULT_KNOTS)
+    exp = {1: 0.007808861, 64: 0.46778646, 128: 0.74364215, 140: 0.7584175, 145: 0.620175, 200: 0.6007686, 254: 0.9919789}
+    for iso, a in exp.items():
+        assert s.getPointOnSpline(iso)[3] == pytest.approx(a, rel=2e-6)
+    for iso, a in DEFAULT_KNOTS:
+        assert s.getPointOnSpline(iso)[3] == np.float32(a)     # exact knots return the knot (:27-28)
+    o = orc.OracleSpline(DEFAULT_KNOTS)
+    assert o.field("coeffs")[:, 3] == pytest.approx([0.5, 0.2857143, 0.26923078, 0.5777778], rel=1e-6)
+    assert o.field("deriv")[:, 3] == pytest.approx([1.1010666, 0.07486665, -0.050533354, 0.85026675], rel=1e-5)
+    assert o.field("d")[:3, 3] == pytest.approx([-0.34206676, 0.6423333, -0.30026668], rel=1e-5)
+
+
+def test_spline_bitwise_equals_oracle():
+    rng = np.random.default_rng(2)
+    for trial in range(20):
+        n = int(rng.integers(2, 9))
+        isos = sorted(rng.choice(np.arange(1, 255), n - 2, replace=False).tolist()) if n > 2 else []
+        knots = [(0, tuple(rng.random(4).tolist()))] + [(int(i), tuple(rng.random(4).tolist())) for i in isos] + [(255, tuple(rng.random(4).tolist()))]
+        s, o = host.CubicSpline(knots), orc.OracleSpline(knots)
+        for iso in range(256):
+            assert np.array_equal(s.getPointOnSpline(iso).view(np.uint32), o.eval_iso(iso).view(np.uint32))
+        for seg in range(n - 1):
+            for t in (0.0, 0.25, 0.5, 1.0):
+                assert np.array_equal(s.getPointOnSplineT(t, seg).view(np.uint32), o.eval_t(t, seg).view(np.uint32))
+        assert np.array_equal(s.bakeAlphaLUT().view(np.uint32), o.alpha_lut().view(np.uint32))
+
+
+def test_alpha_lut_clamps_and_covers_partial_knot_ranges():
+    lut = host.CubicSpline([(20, 0.2), (100, 1.4), (200, -0.3)]).bakeAlphaLUT()
+    assert lut.min() >= 0 and lut.max() <= 1
+    assert (lut[:21] == np.float32(0.2)).all()       # below the first knot: clamped to it
+    assert (lut[200:] == 0).all()                    # above the last knot: clamped (-0.3 -> 0)
+
+
+# ------------------------------------------------------------------ .raw.inf
+
+def test_rawinf_text_format_and_round_trip(tmp_path):
+    fn = str(tmp_path / "vol.raw")
+    assert host.rawinf_write(fn, (64, 48, 40), (1.0, 1.5, 2.0))
+    # RendererCore.cpp:311-315
+    assert open(fn + ".inf").read() == "#dimensions\n64 48 40\n\n#voxel-spacing\n1 1.5 2\n"
+    rc, dims, sp, _, _ = host.rawinf_read(fn)
+    assert rc == 1 and dims == (64, 48, 40) and sp == (1.0, 1.5, 2.0)
+    assert host.rawinf_read(str(tmp_path / "missing.raw"))[0] == -1
+
+
+@pytest.mark.parametrize("text,title,frag", [
+    ("#dimensions\n\n#voxel-spacing\n1 1 1\n", "Invalid .raw.inf file!", "Dimensions for Volume Data not provided"),
+    ("#dimensions\n4 4 4\n#voxel-spacing\n\n", "Invalid .raw.inf file!", "Aspect Ratio for Volume Data not provided"),
+    ("#voxel-spacing\n1 1 1\n", "Invalid .raw.inf file!", "#dimesnsions"),
+    ("#dimensions\n4 4 4\n", "Invalid .raw.inf file!", "#voxel-spacing"),
+])
+def test_rawinf_errors_use_the_reference_messages(tmp_path, text, title, frag):
+    fn = str(tmp_path / "v.raw")
+    open(fn + ".inf", "w").write(text)
+    rc, _, _, t, m = host.rawinf_read(fn)
+    assert rc == 0 and t == title and frag in m          # RendererCore.cpp:264-301
+
+
+# ------------------------------------------------------------------ image writers
+
+def _png_pixels(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])
+        assert zlib.crc32(typ + body) == crc
+        if typ == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", body[:10])
+            assert (depth, ctype) == (8, 2)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    data = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert (data[:, 0] == 0).all()
+    return data[:, 1:].reshape(h, w, 3)
+
+
+def test_png_bmp_ppm_writers(tmp_path):
+    rng = np.random.default_rng(4)
+    for (h, w) in ((5, 7), (300, 251)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        p = str(tmp_path / "a.png")
+        assert host.write_image(p, ".png", img)
+        assert np.array_equal(_png_pixels(p), img)
+        p = str(tmp_path / "a.ppm")
+        assert host.write_image(p, ".ppm", img)
+        raw = open(p, "rb").read()
+        hdr = f"P6\n{w} {h}\n255\n".encode()
+        assert raw.startswith(hdr) and raw[len(hdr):] == img.tobytes()
+        p = str(tmp_path / "a.bmp")
+        assert host.write_image(p, ".bmp", img)
+        raw = open(p, "rb").read()
+        assert raw[:2] == b"BM" and struct.unpack("<ii", raw[18:26]) == (w, h)
+        stride = (w * 3 + 3) & ~3
+        rows = np.frombuffer(raw[54:], np.uint8).reshape(h, stride)[:, :w * 3].reshape(h, w, 3)
+        assert np.array_equal(rows[::-1, :, ::-1], img)      # bottom-up, BGR
+    assert not host.write_image(str(tmp_path / "a.jpg"), ".jpg", img)
