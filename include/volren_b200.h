@@ -45,8 +45,13 @@ typedef enum vr_status {
 
 enum { VR_FILTER_NEAREST = 0, VR_FILTER_TRILINEAR = 1 };
 
-/* kernel selection (all produce bit-identical images) */
-enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2 };
+/* kernel selection (all produce bit-identical images):
+ *   DIRECT   one thread per ray, texels straight from HBM through L1/L2; handles every mode
+ *   FAST     same data path, issue-slot-optimised loop (DVR, default view, no TF)
+ *   WINDOWED persistent screen-tile CTAs marching through TMA-staged shared-memory windows
+ *   AUTO     the fastest kernel that covers the frame's parameters
+ * A request the frame's parameters do not allow falls back to DIRECT. */
+enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2, VR_KERNEL_FAST = 3 };
 
 typedef struct vr_context vr_context;
 

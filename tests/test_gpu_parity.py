@@ -26,7 +26,8 @@ def run_product(vox, dims, voxel_size, cam, W, H, vkw, kernel=vb.KERNEL_AUTO, pa
 
 
 @pytest.mark.parametrize("cid", [c[0] for c in scenarios.CASES])
-@pytest.mark.parametrize("kernel", [vb.KERNEL_DIRECT, vb.KERNEL_AUTO], ids=["direct", "auto"])
+@pytest.mark.parametrize("kernel", [vb.KERNEL_DIRECT, vb.KERNEL_AUTO, vb.KERNEL_FAST, vb.KERNEL_WINDOWED],
+                         ids=["direct", "auto", "fast", "windowed"])
 def test_case_matches_oracle(cid, kernel):
     _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
     vox, dims, bpv, vs = scenarios.volume(vname)
@@ -53,6 +54,28 @@ def test_golden_fixture(cid, golden_dir):
     _, vkw = scenarios.split_kwargs(kw)
     img, _ = run_product(vox, dims, vs, cam, W, H, vkw)
     compare(img, g["rgba"], "golden " + cid)
+
+
+@pytest.mark.parametrize("vname,cname,kw", [
+    ("mix64_u8", "K0", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.3, min_val=20, max_val=220, filter=1)),
+    ("mix_64x64x32_u16", "K1", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1)),
+    ("rand_40x56x33_u16", "K2", dict(alpha_scale=0.03, min_val=100, max_val=4000, filter=1)),
+])
+def test_optimised_kernels_really_run_and_match(vname, cname, kw):
+    """The FAST and WINDOWED kernels are the ones selected (no silent fallback to DIRECT) for
+    frames they cover, and both reproduce the oracle bit for bit."""
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    cam = scenarios.camera(cname)
+    W, H = 320, 200
+    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
+    for kernel in (vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_AUTO):
+        img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
+        if kernel != vb.KERNEL_AUTO:
+            assert st.kernel_used == kernel, f"requested kernel {kernel}, ran {st.kernel_used}"
+        else:
+            assert st.kernel_used in (vb.KERNEL_FAST, vb.KERNEL_WINDOWED)
+        compare(img, ref, f"{vname}/{cname}/kernel{kernel}")
 
 
 def test_counters_and_distinct_voxels_match_oracle():
@@ -204,6 +227,12 @@ def test_full_size_1024_cube_sampled_rows():
         ctx.set_camera(cam)
         ctx.set_params(vb.default_params(**kw))
         img, st = ctx.render()
+        for kernel in (vb.KERNEL_DIRECT, vb.KERNEL_WINDOWED):      # every kernel, same bits, at full size
+            ctx.set_params(vb.default_params(kernel=kernel, **kw))
+            other, st2 = ctx.render()
+            assert st2.kernel_used == kernel
+            assert np.array_equal(other.view(np.uint32), img.view(np.uint32))
+        ctx.set_params(vb.default_params(**kw))
         # 2-way partition of the same frame
         acc = np.zeros_like(img)
         for rank in range(2):

@@ -102,9 +102,14 @@ def test_gui_session_pvm_uint16_plus1000_rule(tmp_path, golden_dir):
     ref, _ = oracle_frame(core.camera_ubo(), vox, dims, 2, W, H, voxel_size=(1.0, 1.0, 1.5), alpha_scale=0.1,
                           min_val=1000, max_val=2500, filter=0)
     compare(core.readFrame(), ref, "16-bit pvm")
-    # histogram: 0..100, the reference's normalisation
+    # histogram: RendererCore.cpp:386-405 -- bin = round(v*255/max), bin 0 skipped, normalised by
+    # max(dataset max value, largest bin count) (the reference re-uses `max_value`)
     h = core.histogram()
-    assert h.max() == pytest.approx(100.0) and h[0] == 0
+    x = vox.astype(np.float32) * np.float32(255.0) / np.float32(vox.max())
+    b = np.trunc(x); b = (b + ((x - b) >= np.float32(0.5))).astype(np.int64)
+    counts = np.bincount(b, minlength=256).astype(np.float32); counts[0] = 0
+    expect = counts * np.float32(100.0) / np.float32(max(int(vox.max()), int(counts.max())))
+    assert np.array_equal(h, expect) and h[0] == 0
 
 
 def test_load_errors_surface_as_popups(tmp_path):

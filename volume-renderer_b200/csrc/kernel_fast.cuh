@@ -1,0 +1,303 @@
+// kernel_fast.cuh -- issue-slot-optimised form of the reference march for the common case
+// (DVR, default view, no transfer function, ordered window, alpha_scale >= 0).
+//
+// Same correctly-rounded operation sequence as march_device.cuh / the oracle -- results are
+// bit-identical -- but arranged for the B200 SM, where this loop is instruction-issue bound
+// (profiles/r01_*): two rays (horizontally adjacent pixels) per thread with every IEEE
+// add/mul/fma issued as ONE packed Blackwell f32x2 instruction (FADD2/FMUL2/FFMA2) for both
+// rays; texel fetch from the edge-replicated volume without clamps; u16->f32 through the
+// exponent-bias trick with the x-differences taken on the biased values (exact); range tests
+// on the float bit patterns with 3-input integer max; divisions by loop-invariant divisors
+// through the device-verified Markstein sequence.
+#pragma once
+
+#include "march_device.cuh"
+
+namespace vr {
+
+typedef unsigned long long u64;
+
+// ---- packed pair of floats: lane .x = ray 0 (even pixel), lane .y = ray 1 (odd pixel) -------
+struct f2 { u64 v; };
+__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 splat2(float a) { return mk2(a, a); }
+__device__ __forceinline__ float lo(f2 p) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return a; }
+__device__ __forceinline__ float hi(f2 p) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return b; }
+__device__ __forceinline__ f2 fadd(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 fsub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 fmul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 ffma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+// ptxas (12.9) contracts mul.rn.f32x2 -> add/sub.rn.f32x2 into FFMA2 even under -fmad=false
+// (it honours the explicit .rn only on scalar ops).  Wherever the shader has an UNFUSED
+// product feeding a sum, the sum is therefore issued as two scalar add.rn.f32.
+__device__ __forceinline__ f2 fadd_after_mul(f2 a, f2 prod) { return mk2(__fadd_rn(lo(a), lo(prod)), __fadd_rn(hi(a), hi(prod))); }
+__device__ __forceinline__ f2 fsub_after_mul(f2 a, f2 prod) { return mk2(__fsub_rn(lo(a), lo(prod)), __fsub_rn(hi(a), hi(prod))); }
+
+// scalar "pair" of one ray so the same march body serves 1 and 2 rays per thread
+struct f1 { float v; };
+__device__ __forceinline__ f1 fadd(f1 a, f1 b) { return {__fadd_rn(a.v, b.v)}; }
+__device__ __forceinline__ f1 fsub(f1 a, f1 b) { return {__fsub_rn(a.v, b.v)}; }
+__device__ __forceinline__ f1 fmul(f1 a, f1 b) { return {__fmul_rn(a.v, b.v)}; }
+__device__ __forceinline__ f1 ffma(f1 a, f1 b, f1 c) { return {__fmaf_rn(a.v, b.v, c.v)}; }
+__device__ __forceinline__ f1 fadd_after_mul(f1 a, f1 prod) { return {__fadd_rn(a.v, prod.v)}; }
+__device__ __forceinline__ f1 fsub_after_mul(f1 a, f1 prod) { return {__fsub_rn(a.v, prod.v)}; }
+
+template <typename L> struct Lanes;
+template <> struct Lanes<f1> {
+    static constexpr int N = 1;
+    static __device__ __forceinline__ f1 splat(float a) { return {a}; }
+    static __device__ __forceinline__ float get(f1 p, int) { return p.v; }
+    template <typename F> static __device__ __forceinline__ f1 map(F f) { return {f(0)}; }
+};
+template <> struct Lanes<f2> {
+    static constexpr int N = 2;
+    static __device__ __forceinline__ f2 splat(float a) { return splat2(a); }
+    static __device__ __forceinline__ float get(f2 p, int i) { return i == 0 ? lo(p) : hi(p); }
+    template <typename F> static __device__ __forceinline__ f2 map(F f) { return mk2(f(0), f(1)); }
+};
+
+enum WinMode : int {
+    WIN_CLAMP = 0,     // clamp to [min,max], subtract min, divide by range (any ordered window)
+    WIN_COVERS0 = 1    // min == 0 and every voxel value <= max: clamp and subtraction are no-ops
+};
+
+struct FastArgs {
+    const void* vol;
+    uint32_t pitch;            // elements per row of the padded volume
+    uint32_t slice_lo;         // pitch * (Ny+2), elements (< 2^32 checked on the host)
+    float* out;
+    int local_rows;
+};
+
+// a / d, d loop invariant, packed or scalar
+template <int MODE, typename L>
+__device__ __forceinline__ L div_by_l(L a, float d, float inv)
+{
+    const L vinv = Lanes<L>::splat(inv);
+    if (MODE == DIV_RECIP_EXACT) return fmul(a, vinv);
+    const L q0 = fmul(a, vinv);
+    const L r = ffma(Lanes<L>::splat(-d), q0, a);
+    return ffma(r, vinv, q0);
+}
+
+enum FloorMode : int {
+    FLOOR_XU2 = 0,     // FRND.FLOOR + F2I.FLOOR            (2 conversion-pipe ops per axis)
+    FLOOR_XU1 = 1,     // F2I.FLOOR + I2FP                   (1 conversion-pipe op per axis)
+    FLOOR_MAGIC = 2    // 1.5*2^23 rounding trick            (no conversion-pipe op)
+};
+
+// f -> (w = f - floor(f), floor(f) + 1 as int), all lanes.  Every variant returns exactly
+// floorf(f) and the single-rounded difference f - floorf(f) for |f| < 2^22.
+template <int FM, typename L>
+__device__ __forceinline__ void floor_frac_idx(L f, L& w, int idx_plus1[2])
+{
+    typedef Lanes<L> LN;
+    if (FM == FLOOR_XU2) {
+        const L fl = LN::map([&](int l) { return floorf(LN::get(f, l)); });
+        w = fsub(f, fl);
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) idx_plus1[l] = __float2int_rd(LN::get(f, l)) + 1;
+    } else if (FM == FLOOR_XU1) {
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) idx_plus1[l] = __float2int_rd(LN::get(f, l));
+        const L fl = LN::map([&](int l) { return (float)idx_plus1[l]; });
+        w = fsub(f, fl);
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) idx_plus1[l] += 1;
+    } else {
+        const L M = LN::splat(12582912.0f);                // 1.5 * 2^23: t = M + RN(f) exactly
+        const L t = fadd(f, M);
+        const L r = fsub(t, M);                             // RN(f)
+        bool up[2];
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) up[l] = LN::get(r, l) > LN::get(f, l);   // rounded up: floor = RN(f) - 1
+        const L adj = LN::map([&](int l) { return up[l] ? 1.0f : 0.0f; });
+        w = fsub(f, fsub(r, adj));
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l)
+            idx_plus1[l] = __float_as_int(LN::get(t, l)) - 0x4B400000 + (up[l] ? 0 : 1);
+    }
+}
+
+// VolumeRenderer.cs:121 for all lanes: nearest i = floor(u*N) (+1 padded, no clamp needed), or
+// the trilinear extension f = fma(u,N,-0.5), lerp(a,b,w) = fma(w, b-a, a), x then y then z.
+template <typename T, int FILTER, int FM, typename L>
+__device__ __forceinline__ L sample_lanes(const T* __restrict__ vol, uint32_t pitch, uint32_t slice,
+                                          const float dimf[3], L tx, L ty, L tz)
+{
+    typedef Lanes<L> LN;
+    if (FILTER == VR_FILTER_NEAREST) {
+        const L ux = fmul(tx, LN::splat(dimf[0])), uy = fmul(ty, LN::splat(dimf[1])), uz = fmul(tz, LN::splat(dimf[2]));
+        return LN::map([&](int l) {
+            const int jx = __float2int_rd(LN::get(ux, l)) + 1, jy = __float2int_rd(LN::get(uy, l)) + 1,
+                      jz = __float2int_rd(LN::get(uz, l)) + 1;
+            const uint32_t e = (uint32_t)jz * slice + ((uint32_t)jy * pitch + (uint32_t)jx);
+            return u2f((uint32_t)__ldg(vol + e));
+        });
+    }
+    const L mhalf = LN::splat(-0.5f);
+    L wx, wy, wz;
+    int jx[2], jy[2], jz[2];
+    floor_frac_idx<FM>(ffma(tx, LN::splat(dimf[0]), mhalf), wx, jx);
+    floor_frac_idx<FM>(ffma(ty, LN::splat(dimf[1]), mhalf), wy, jy);
+    floor_frac_idx<FM>(ffma(tz, LN::splat(dimf[2]), mhalf), wz, jz);
+    // biased floats 2^23 + v: differences of biased values are exact, so only the four
+    // x-low corners need un-biasing
+    float b[2][8];
+#pragma unroll
+    for (int l = 0; l < LN::N; ++l) {
+        // 32-bit element index: the host only selects this kernel when the padded volume has
+        // fewer than 2^32 voxels
+        const uint32_t e00 = (uint32_t)jz[l] * slice + ((uint32_t)jy[l] * pitch + (uint32_t)jx[l]);
+        const uint32_t e10 = e00 + pitch, e01 = e00 + slice, e11 = e01 + pitch;
+        b[l][0] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e00));
+        b[l][1] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e00 + 1));
+        b[l][2] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e10));
+        b[l][3] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e10 + 1));
+        b[l][4] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e01));
+        b[l][5] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e01 + 1));
+        b[l][6] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e11));
+        b[l][7] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e11 + 1));
+    }
+    L v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = LN::map([&](int l) { return b[l][k]; });
+    const L B = LN::splat(8388608.0f);
+    const L c00 = ffma(wx, fsub(v[1], v[0]), fsub(v[0], B));
+    const L c10 = ffma(wx, fsub(v[3], v[2]), fsub(v[2], B));
+    const L c01 = ffma(wx, fsub(v[5], v[4]), fsub(v[4], B));
+    const L c11 = ffma(wx, fsub(v[7], v[6]), fsub(v[6], B));
+    const L c0 = ffma(wy, fsub(c10, c00), c00);
+    const L c1 = ffma(wy, fsub(c11, c01), c01);
+    return ffma(wz, fsub(c1, c0), c0);
+}
+
+// One march loop for NL = Lanes<L>::N rays advancing in lock step.  Returns with `done` bits
+// set for rays that have finished (left the box or reached the opacity threshold); a ray
+// whose partner finished first is completed by a scalar call of the same function.
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, typename L>
+__device__ __forceinline__ unsigned march_lanes(const FrameConsts& fc, const T* __restrict__ vol, uint32_t pitch,
+                                                uint32_t slice, L pos[3], const L dstep[3], L& C, L& A, int& iter)
+{
+    typedef Lanes<L> LN;
+    const L half0 = LN::splat(fc.half_len[0]), half1 = LN::splat(fc.half_len[1]), half2 = LN::splat(fc.half_len[2]);
+    const L one = LN::splat(1.0f);
+    const L alpha = LN::splat(fc.alpha_scale);
+    const L vfmin = LN::splat(fc.fmin);
+    unsigned done = 0;
+    for (; iter < 10000; ++iter) {
+        // cartesianToTextureCoord, VolumeRenderer.cs:175-192
+        const L tx = div_by_l<TCDIV>(fadd(pos[0], half0), fc.denom[0], fc.inv_denom[0]);
+        const L ty = div_by_l<TCDIV>(fadd(pos[1], half1), fc.denom[1], fc.inv_denom[1]);
+        const L tz = fsub_after_mul(one, div_by_l<TCDIV>(fadd(pos[2], half2), fc.denom[2], fc.inv_denom[2]));
+        // :118 -- 0 <= t <= 1 on all three and A < 0.95, on the bit patterns (no -0, no NaN:
+        // the camera block is validated finite and alpha_scale >= 0 on this path)
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) {
+            const unsigned m = max(max(__float_as_uint(LN::get(tx, l)), __float_as_uint(LN::get(ty, l))),
+                                   __float_as_uint(LN::get(tz, l)));
+            if (m > 0x3F800000u || __float_as_uint(LN::get(A, l)) >= 0x3F733333u) done |= 1u << l;
+        }
+        if (done) break;
+
+        const L s = sample_lanes<T, FILTER, FM>(vol, pitch, slice, fc.dimf, tx, ty, tz);
+        // :122-124
+        L v;
+        if (WIN == WIN_COVERS0) {
+            v = div_by_l<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        } else {
+            const L cl = LN::map([&](int l) { return fminf(fmaxf(LN::get(s, l), fc.fmin), fc.fmax); });
+            v = div_by_l<DIV_MARKSTEIN>(fsub(cl, vfmin), fc.frange, fc.inv_frange);
+        }
+        // :130-132 (the bottom `dest.a > 0.99` break of :134 is subsumed by the :118 test of
+        // the next iteration: nothing but `pos` changes in between)
+        const L a = fmul(v, alpha);
+        const L c = fmul(v, a);
+        const L t = fsub(one, A);
+        C = fadd_after_mul(C, fmul(c, t));
+        A = fadd_after_mul(A, fmul(a, t));
+        pos[0] = fadd(pos[0], dstep[0]);
+        pos[1] = fadd(pos[1], dstep[1]);
+        pos[2] = fadd(pos[2], dstep[2]);
+    }
+    return done;
+}
+
+constexpr int FAST_THREADS = 256;
+
+// RAYS = 2: a thread owns pixels (2i, 2i+1) of a row; a warp covers 16x4 pixels, a CTA 64x8.
+// RAYS = 1: a warp covers 8x4 pixels, a CTA 32x8 (same as the baseline kernel).
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS>
+__global__ void __launch_bounds__(FAST_THREADS)
+march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ FastArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);       // thread column
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int px0 = tx * RAYS;
+    if (px0 >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const T* __restrict__ vol = static_cast<const T*>(args.vol);
+    const uint32_t pitch = args.pitch, slice = args.slice_lo;
+    const int orow = fc.compact ? lrow : py;
+    float4* out = reinterpret_cast<float4*>(args.out) + (size_t)orow * fc.W;
+
+    if (RAYS == 1) {
+        const RaySetup r = setup_ray(fc, px0, py);
+        f1 C{0.0f}, A{0.0f};
+        if (r.hit) {
+            f1 pos[3], ds[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                pos[i].v = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
+                ds[i].v = __fmul_rn(r.dir[i], fc.step);
+            }
+            int iter = 0;
+            march_lanes<T, FILTER, TCDIV, WIN, FM, f1>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        }
+        out[px0] = make_float4(C.v, C.v, C.v, A.v);
+        return;
+    }
+
+    // ---- two rays ----
+    const bool have1 = (px0 + 1) < fc.W;
+    const RaySetup r0 = setup_ray(fc, px0, py);
+    const RaySetup r1 = setup_ray(fc, have1 ? px0 + 1 : px0, py);
+    float p0[3], p1[3], d0[3], d1[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        p0[i] = __fadd_rn(__fadd_rn(r0.org[i], __fmul_rn(r0.dir[i], r0.t_min)), __fmul_rn(r0.dir[i], 0.000001f));
+        p1[i] = __fadd_rn(__fadd_rn(r1.org[i], __fmul_rn(r1.dir[i], r1.t_min)), __fmul_rn(r1.dir[i], 0.000001f));
+        d0[i] = __fmul_rn(r0.dir[i], fc.step);
+        d1[i] = __fmul_rn(r1.dir[i], fc.step);
+    }
+    float C0 = 0.f, A0 = 0.f, C1 = 0.f, A1 = 0.f;
+    unsigned alive = (r0.hit ? 1u : 0u) | ((r1.hit && have1) ? 2u : 0u);
+    int iter = 0;
+    if (alive == 3u) {
+        f2 pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pos[i] = mk2(p0[i], p1[i]); ds[i] = mk2(d0[i], d1[i]); }
+        f2 C = mk2(0.f, 0.f), A = mk2(0.f, 0.f);
+        const unsigned done = march_lanes<T, FILTER, TCDIV, WIN, FM, f2>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        C0 = lo(C); C1 = hi(C); A0 = lo(A); A1 = hi(A);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p0[i] = lo(pos[i]); p1[i] = hi(pos[i]); }
+        alive &= ~done;
+        if (iter >= 10000) alive = 0;
+    }
+    if (alive) {   // finish whichever ray is still marching (both rays share `iter` so far)
+        const bool second = (alive & 2u) != 0;
+        f1 pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pos[i].v = second ? p1[i] : p0[i]; ds[i].v = second ? d1[i] : d0[i]; }
+        f1 C{second ? C1 : C0}, A{second ? A1 : A0};
+        march_lanes<T, FILTER, TCDIV, WIN, FM, f1>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        if (second) { C1 = C.v; A1 = A.v; } else { C0 = C.v; A0 = A.v; }
+    }
+    out[px0] = make_float4(C0, C0, C0, A0);
+    if (have1) out[px0 + 1] = make_float4(C1, C1, C1, A1);
+}
+
+}  // namespace vr

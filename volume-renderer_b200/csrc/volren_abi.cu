@@ -17,6 +17,7 @@
 #include "frame.h"
 #include "march_device.cuh"
 #include "kernel_direct.cuh"
+#include "kernel_fast.cuh"
 #include "kernel_windowed.cuh"
 #include "kernels_aux.cuh"
 
@@ -203,23 +204,61 @@ int launch_direct(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStrea
                        : launch_direct_t<uint16_t, false>(c, plan, args, s);
 }
 
+template <typename T>
+int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    using namespace vr;
+    FastArgs a{};
+    a.vol = c->d_vol; a.pitch = c->pitch; a.slice_lo = (uint32_t)c->slice; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 block(FAST_THREADS), grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
+    const FrameConsts& fc = plan.fc;
+    const bool tri = fc.filter == VR_FILTER_TRILINEAR, recip = plan.tcdiv == DIV_RECIP_EXACT, cov = win == WIN_COVERS0;
+#define VR_FAST(F, D, W) march_fast_kernel<T, F, D, W, FLOOR_XU1, 1><<<grid, block, 0, s>>>(fc, a)
+    if (tri) {
+        if (recip) { if (cov) VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_COVERS0); else VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_CLAMP); }
+        else       { if (cov) VR_FAST(VR_FILTER_TRILINEAR, DIV_MARKSTEIN, WIN_COVERS0);   else VR_FAST(VR_FILTER_TRILINEAR, DIV_MARKSTEIN, WIN_CLAMP); }
+    } else {
+        if (recip) { if (cov) VR_FAST(VR_FILTER_NEAREST, DIV_RECIP_EXACT, WIN_COVERS0); else VR_FAST(VR_FILTER_NEAREST, DIV_RECIP_EXACT, WIN_CLAMP); }
+        else       { if (cov) VR_FAST(VR_FILTER_NEAREST, DIV_MARKSTEIN, WIN_COVERS0);   else VR_FAST(VR_FILTER_NEAREST, DIV_MARKSTEIN, WIN_CLAMP); }
+    }
+#undef VR_FAST
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
 // the march: returns which kernel ran
 int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, uint32_t* used,
                  uint32_t* launches)
 {
+    const vr::FrameConsts& fc = plan.fc;
+    const uint64_t padded_voxels = c->slice * (uint64_t)(c->dim[2] + 2);
+    // the optimised kernels cover: DVR, default view, no TF, ordered window with a verified
+    // Markstein divisor, alpha_scale >= 0 (range tests on bit patterns), 32-bit texel indices,
+    // correctly rounded tex-coord division without div.rn
+    const bool fast_ok = !plan.generic && plan.tcdiv != vr::DIV_IEEE && c->params.alpha_scale >= 0.0f &&
+                         padded_voxels < (1ull << 32);
+    const bool windowed_ok = fast_ok && vr::windowed_supported(fc, c->bpv, padded_voxels);
+    const int win = (c->params.min_val == 0 && c->have_stats && c->stats.max_value <= c->params.max_val)
+                        ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
     int want = c->params.kernel;
-    const bool windowed_ok = !plan.generic && vr::windowed_supported(plan.fc, c->bpv);
-    if (want == VR_KERNEL_AUTO) want = windowed_ok ? VR_KERNEL_WINDOWED : VR_KERNEL_DIRECT;
-    if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_AUTO) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_FAST && !fast_ok) want = VR_KERNEL_DIRECT;
+    *launches = 1;
     if (want == VR_KERNEL_WINDOWED) {
-        int rc = vr::launch_windowed(c->win, plan.fc, c->d_vol, c->bpv, c->pitch, c->slice, d_out,
-                                     plan.local_rows, c->sm_count, s, launches);
-        if (rc != 0) return cuda_fail(cudaGetLastError(), vr::windowed_last_error());
-        *used = VR_KERNEL_WINDOWED;
-        return VR_OK;
+        int rc = c->bpv == 1
+            ? vr::launch_windowed_t<uint8_t>(c->win, fc, c->d_vol, c->pitch, c->slice, c->dim[1], c->dim[2], d_out, plan.local_rows, c->sm_count, plan.tcdiv, win, s, false)
+            : vr::launch_windowed_t<uint16_t>(c->win, fc, c->d_vol, c->pitch, c->slice, c->dim[1], c->dim[2], d_out, plan.local_rows, c->sm_count, plan.tcdiv, win, s, false);
+        if (rc == 0) { *used = VR_KERNEL_WINDOWED; return VR_OK; }
+        // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
+        cudaGetLastError();
+        want = VR_KERNEL_FAST;
+    }
+    if (want == VR_KERNEL_FAST) {
+        *used = VR_KERNEL_FAST;
+        return c->bpv == 1 ? launch_fast_t<uint8_t>(c, plan, d_out, s, win) : launch_fast_t<uint16_t>(c, plan, d_out, s, win);
     }
     *used = VR_KERNEL_DIRECT;
-    *launches = 1;
     return launch_direct(c, plan, d_out, s);
 }
 
@@ -476,7 +515,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_WINDOWED)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_FAST)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         VR_CUDA(cudaSetDevice(c->device));
