@@ -39,7 +39,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mrays/sec at 1920x1080, 1024^3 uint16, 1024 steps"
 UNIT = "Mrays/s"
-TILE_ROWS = 8
+TILE_ROWS = 16
 
 
 def parse_args():
@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)],
+                                          "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -315,7 +315,7 @@ def run_ours(args):
     avg_kernel_ms = float(np.mean(timed_kernel_ms))
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel"}.get(used[0], "?"),
+            "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel", 3: "march_fast_kernel"}.get(used[0], "?"),
             "kernel_ms_avg": avg_kernel_ms}
     if counted is not None:
         owned_px = sum(min(TILE_ROWS, H - t0_ * TILE_ROWS) for t0_ in range(rank, (H + TILE_ROWS - 1) // TILE_ROWS, world)) * W
