@@ -30,7 +30,9 @@ static const float K2[21] = {-0.9396927f,0,0.34202015f,0, 0.11697778f,0.9396926f
 
 struct Lab {
     int W = 1920, H = 1080, N = 1024;
+    int rows = 1080;          // local rows rendered (emulated rank of a partition)
     uint16_t* d_pad = nullptr; uint32_t pitch = 0; uint64_t slice = 0;
+    uint32_t* d_pairs = nullptr;
     float *d_ref = nullptr, *d_out = nullptr;
     FrameConsts fc;
     cudaEvent_t e0, e1;
@@ -68,15 +70,32 @@ static void check(Lab& L, const char* name, float ms, double gsamples)
 
 static const char* g_only = nullptr;   // run only variants whose name contains this
 
-template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS>
+static int g_persist = 0;               // >0: persistent grid with this many CTAs per SM
+static int g_sms = 148;
+static int g_center = 0;
+static unsigned int* g_counter = nullptr;
+
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS, bool PAIRS = false, bool PIPE = false>
 static void run_fast(Lab& L, const char* name, double samples)
 {
     if (g_only && !strstr(name, g_only)) return;
     FastArgs a{};
-    a.vol = L.d_pad; a.pitch = L.pitch; a.slice_lo = (uint32_t)L.slice; a.out = L.d_out; a.local_rows = L.H;
+    a.vol = PAIRS ? (const void*)L.d_pairs : (const void*)L.d_pad; a.pitch = L.pitch; a.slice_lo = (uint32_t)L.slice; a.out = L.d_out; a.local_rows = L.rows;
     const int cols = (L.W + RAYS - 1) / RAYS;
-    dim3 grid((cols + 31) / 32, (L.H + 7) / 8), block(FAST_THREADS);
-    const float ms = time_kernel(L, [&] { march_fast_kernel<T, FILTER, TCDIV, WIN, FM, RAYS><<<grid, block>>>(L.fc, a); });
+    a.local_rows = L.rows;
+    dim3 grid((cols + 31) / 32, (L.rows + 7) / 8), block(FAST_THREADS);
+    const float ms = time_kernel(L, [&] { march_fast_kernel<T, FILTER, TCDIV, WIN, FM, RAYS, PAIRS, PIPE><<<grid, block>>>(L.fc, a); });
+    check(L, name, ms, samples);
+}
+
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+static void run_packed(Lab& L, const char* name, double samples)
+{
+    if (g_only && !strstr(name, g_only)) return;
+    FastArgs a{};
+    a.vol = L.d_pad; a.pitch = L.pitch; a.slice_lo = (uint32_t)L.slice; a.out = L.d_out; a.local_rows = L.rows;
+    dim3 grid((L.W + 31) / 32, (L.rows + 7) / 8), block(256);
+    const float ms = time_kernel(L, [&] { march_packed_kernel<T, TCDIV, WIN, UNIT, NOCAP><<<grid, block>>>(L.fc, a); });
     check(L, name, ms, samples);
 }
 
@@ -88,7 +107,7 @@ static void run_windowed(Lab& L, const char* name, double samples, int tcdiv, in
     float best = 1e30f;
     for (int i = 0; i < 5; ++i) {
         CK(cudaEventRecord(L.e0));
-        if (launch_windowed_t<T>(st, L.fc, L.d_pad, L.pitch, L.slice, L.N, L.N, L.d_out, L.H, sms, tcdiv, win, 0, stats, ctas_per_sm) != 0) {
+        if (launch_windowed_t<T>(st, L.fc, L.d_pad, L.pitch, L.slice, L.N, L.N, L.d_out, L.rows, sms, tcdiv, win, 0, stats, ctas_per_sm) != 0) {
             printf("%s: launch failed: %s\n", name, st.err); return;
         }
         CK(cudaEventRecord(L.e1));
@@ -112,6 +131,9 @@ int main(int argc, char** argv)
     const int filter = argc > 3 ? atoi(argv[3]) : 1;
     if (argc > 4) L.N = atoi(argv[4]);
     if (argc > 5) g_only = argv[5];
+    const int world = argc > 6 ? atoi(argv[6]) : 1;
+    if (argc > 7) g_persist = atoi(argv[7]);
+    if (argc > 8) g_center = atoi(argv[8]);
     const float* cam = !strcmp(camname, "K0") ? K0 : (!strcmp(camname, "K1") ? K1 : K2);
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     printf("%s, %d SMs; workload %d^3 u16, %dx%d, camera %s, alpha %g, filter %d\n", prop.name, prop.multiProcessorCount,
@@ -125,6 +147,8 @@ int main(int argc, char** argv)
     L.slice = (uint64_t)L.pitch * (N + 2);
     CK(cudaMalloc(&L.d_pad, L.slice * (N + 2) * 2 + 256));
     pad_volume_kernel<uint16_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pad, N, N, N, L.pitch);
+    CK(cudaMalloc(&L.d_pairs, L.slice * (N + 2) * 4 + 256));
+    pad_pairs_kernel<uint16_t, uint32_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pairs, N, N, N, L.pitch);
     CK(cudaDeviceSynchronize());
     CK(cudaFree(d_src));
     CK(cudaMalloc(&L.d_ref, (size_t)L.W * L.H * 16)); CK(cudaMalloc(&L.d_out, (size_t)L.W * L.H * 16));
@@ -134,15 +158,18 @@ int main(int argc, char** argv)
     const int32_t dim[3] = {N, N, N}; const float vs[3] = {1, 1, 1};
     memset(&L.fc, 0, sizeof L.fc);
     compute_frame_consts(L.fc, L.W, L.H, dim, vs, cam, p);
-    L.fc.rank = 0; L.fc.world = 1; L.fc.tile_rows = 8; L.fc.compact = 0;
+    L.fc.rank = 0; L.fc.world = world; L.fc.tile_rows = 16; L.fc.compact = 0;
+    L.rows = ((L.H + 15) / 16 + world - 1) / world * 16;
+    g_sms = prop.multiProcessorCount;
+    printf("emulating rank 0 of %d: %d local rows; persistent CTAs/SM: %d\n", world, L.rows, g_persist);
     printf("tc_div_mode %d (0 = exact reciprocal), denom %g %g %g, step %g\n", L.fc.tc_div_mode, L.fc.denom[0], L.fc.denom[1], L.fc.denom[2], L.fc.step);
 
     // sample count through the instrumented kernel (also the reference image source)
     unsigned long long* d_cnt; CK(cudaMalloc(&d_cnt, 24)); CK(cudaMemset(d_cnt, 0, 24));
     unsigned int* d_bits; CK(cudaMalloc(&d_bits, (nvox + 31) / 32 * 4)); CK(cudaMemset(d_bits, 0, (nvox + 31) / 32 * 4));
-    DirectArgs da{}; da.vol = L.d_pad; da.pitch = L.pitch; da.slice = L.slice; da.out = L.d_ref; da.local_rows = L.H;
+    DirectArgs da{}; da.vol = L.d_pad; da.pitch = L.pitch; da.slice = L.slice; da.out = L.d_ref; da.local_rows = L.rows;
     da.touch_bits = d_bits; da.counters = d_cnt;
-    dim3 dgrid((L.W + 31) / 32, (L.H + 7) / 8), dblock(256);
+    dim3 dgrid((L.W + 31) / 32, (L.rows + 7) / 8), dblock(256);
     march_direct_kernel<uint16_t, 0, DIV_IEEE, true, true><<<dgrid, dblock>>>(L.fc, da);
     CK(cudaDeviceSynchronize());
     unsigned long long cnt[3]; CK(cudaMemcpy(cnt, d_cnt, 24, cudaMemcpyDeviceToHost));
@@ -165,6 +192,19 @@ int main(int argc, char** argv)
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (auto occupancy)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 0, prop.multiProcessorCount);
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (2 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 2, prop.multiProcessorCount);
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (4 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 4, prop.multiProcessorCount);
+        run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, false, false>(L, "packed-in-ray covers0", samples);
+        run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, false>(L, "packed-in-ray covers0 UNIT", samples);
+        run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, true>(L, "packed-in-ray covers0 UNIT NOCAP", samples);
+        run_packed<uint16_t, DIV_RECIP_EXACT, WIN_CLAMP, false, false>(L, "packed-in-ray clamp", samples);
+        run_packed<uint16_t, DIV_MARKSTEIN, WIN_CLAMP, false, false>(L, "packed-in-ray clamp markstein-tc", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 1, false, true>(L, "pipe u16   1ray  covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 2, false, true>(L, "pipe u16   2rays covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 1, true, true>(L, "pipe pairs 1ray  covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 2, true, true>(L, "pipe pairs 2rays covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_CLAMP, FLOOR_XU1, 1, false, true>(L, "pipe u16   1ray  clamp   floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 1, true>(L, "pairs 1ray  covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 2, true>(L, "pairs 2rays covers0 floor=XU1", samples);
+        run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU2, 2, true>(L, "pairs 2rays covers0 floor=XU2", samples);
         run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU2, 1>(L, "fast 1ray  covers0 floor=XU2", samples);
         run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_XU1, 1>(L, "fast 1ray  covers0 floor=XU1", samples);
         run_fast<uint16_t, 1, DIV_RECIP_EXACT, WIN_COVERS0, FLOOR_MAGIC, 1>(L, "fast 1ray  covers0 floor=MAGIC", samples);

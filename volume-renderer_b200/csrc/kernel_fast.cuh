@@ -121,7 +121,24 @@ __device__ __forceinline__ void floor_frac_idx(L f, L& w, int idx_plus1[2])
 
 // VolumeRenderer.cs:121 for all lanes: nearest i = floor(u*N) (+1 padded, no clamp needed), or
 // the trilinear extension f = fma(u,N,-0.5), lerp(a,b,w) = fma(w, b-a, a), x then y then z.
-template <typename T, int FILTER, int FM, typename L>
+// pair-packed layout: element e of the "pairs" volume holds voxels (x, x+1) of the padded
+// volume in one word (uint32 for 16-bit data, uint16 for 8-bit data): one load per texel row
+template <typename T> struct PairWord;
+template <> struct PairWord<uint16_t> { typedef uint32_t type; };
+template <> struct PairWord<uint8_t>  { typedef uint16_t type; };
+template <typename T> __device__ __forceinline__ void unpack_biased(typename PairWord<T>::type w, float& lo_b, float& hi_b);
+template <> __device__ __forceinline__ void unpack_biased<uint16_t>(uint32_t w, float& lo_b, float& hi_b)
+{
+    lo_b = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610));
+    hi_b = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632));
+}
+template <> __device__ __forceinline__ void unpack_biased<uint8_t>(uint16_t w, float& lo_b, float& hi_b)
+{
+    lo_b = __uint_as_float(__byte_perm((uint32_t)w, 0x4B000000u, 0x7660));
+    hi_b = __uint_as_float(__byte_perm((uint32_t)w, 0x4B000000u, 0x7661));
+}
+
+template <typename T, int FILTER, int FM, bool PAIRS, typename L>
 __device__ __forceinline__ L sample_lanes(const T* __restrict__ vol, uint32_t pitch, uint32_t slice,
                                           const float dimf[3], L tx, L ty, L tz)
 {
@@ -150,6 +167,25 @@ __device__ __forceinline__ L sample_lanes(const T* __restrict__ vol, uint32_t pi
         // fewer than 2^32 voxels
         const uint32_t e00 = (uint32_t)jz[l] * slice + ((uint32_t)jy[l] * pitch + (uint32_t)jx[l]);
         const uint32_t e10 = e00 + pitch, e01 = e00 + slice, e11 = e01 + pitch;
+        if (PAIRS) {
+            const typename PairWord<T>::type* pv = reinterpret_cast<const typename PairWord<T>::type*>(vol);
+            unpack_biased<T>(__ldg(pv + e00), b[l][0], b[l][1]);
+            unpack_biased<T>(__ldg(pv + e10), b[l][2], b[l][3]);
+            unpack_biased<T>(__ldg(pv + e01), b[l][4], b[l][5]);
+            unpack_biased<T>(__ldg(pv + e11), b[l][6], b[l][7]);
+            continue;
+        }
+#if defined(VR_ABLATE) && VR_ABLATE == 1      // lab only: no memory traffic at all
+        for (int k = 0; k < 8; ++k) b[l][k] = __uint_as_float(0x4B000000u | ((e00 + 37u * k) & 0xfffu));
+        continue;
+#elif defined(VR_ABLATE) && VR_ABLATE == 2    // lab only: every lane reads the same 8 texels (broadcast)
+        { const uint32_t u = (e00 & 0u) + 1234567u, u10 = u + pitch, u01 = u + slice, u11 = u01 + pitch;
+          b[l][0] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u)); b[l][1] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u + 1));
+          b[l][2] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u10)); b[l][3] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u10 + 1));
+          b[l][4] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u01)); b[l][5] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u01 + 1));
+          b[l][6] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u11)); b[l][7] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + u11 + 1));
+          continue; }
+#endif
         b[l][0] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e00));
         b[l][1] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e00 + 1));
         b[l][2] = __uint_as_float(0x4B000000u | (uint32_t)__ldg(vol + e10));
@@ -175,7 +211,7 @@ __device__ __forceinline__ L sample_lanes(const T* __restrict__ vol, uint32_t pi
 // One march loop for NL = Lanes<L>::N rays advancing in lock step.  Returns with `done` bits
 // set for rays that have finished (left the box or reached the opacity threshold); a ray
 // whose partner finished first is completed by a scalar call of the same function.
-template <typename T, int FILTER, int TCDIV, int WIN, int FM, typename L>
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, typename L, bool PAIRS = false>
 __device__ __forceinline__ unsigned march_lanes(const FrameConsts& fc, const T* __restrict__ vol, uint32_t pitch,
                                                 uint32_t slice, L pos[3], const L dstep[3], L& C, L& A, int& iter)
 {
@@ -200,7 +236,7 @@ __device__ __forceinline__ unsigned march_lanes(const FrameConsts& fc, const T* 
         }
         if (done) break;
 
-        const L s = sample_lanes<T, FILTER, FM>(vol, pitch, slice, fc.dimf, tx, ty, tz);
+        const L s = sample_lanes<T, FILTER, FM, PAIRS>(vol, pitch, slice, fc.dimf, tx, ty, tz);
         // :122-124
         L v;
         if (WIN == WIN_COVERS0) {
@@ -223,17 +259,259 @@ __device__ __forceinline__ unsigned march_lanes(const FrameConsts& fc, const T* 
     return done;
 }
 
+// ------------------------------------------------------------------------------------------
+// Software-pipelined march.  The texel addresses of sample i+1 depend only on `pos`, never on
+// loaded data; the only data dependence between iterations is the opacity test.  So the loads
+// of sample i+1 are issued BEFORE sample i is interpolated and composited: two samples (four
+// with 2 rays/thread) are in flight per thread, which is what hides the L1-miss latency this
+// loop is otherwise bound by.  Scheduling only -- the operation sequence per sample, and hence
+// every bit of the result, is unchanged.  A prefetch that turns out to be unnecessary (the ray
+// terminated on opacity) is a harmless read inside the padded volume.
+template <typename T, bool PAIRS> struct RawTexels { uint32_t w[PAIRS ? 4 : 8]; };
+
+template <typename T, int FM, bool PAIRS, typename L>
+struct Fetch {
+    L wx, wy, wz;
+    RawTexels<T, PAIRS> raw[2];
+};
+
+// coordinates -> weights + issued loads (trilinear only)
+template <typename T, int FM, bool PAIRS, typename L>
+__device__ __forceinline__ void issue_fetch(const T* __restrict__ vol, uint32_t pitch, uint32_t slice, const float dimf[3],
+                                            L tx, L ty, L tz, Fetch<T, FM, PAIRS, L>& f)
+{
+    typedef Lanes<L> LN;
+    const L mhalf = LN::splat(-0.5f);
+    int jx[2], jy[2], jz[2];
+    floor_frac_idx<FM>(ffma(tx, LN::splat(dimf[0]), mhalf), f.wx, jx);
+    floor_frac_idx<FM>(ffma(ty, LN::splat(dimf[1]), mhalf), f.wy, jy);
+    floor_frac_idx<FM>(ffma(tz, LN::splat(dimf[2]), mhalf), f.wz, jz);
+#pragma unroll
+    for (int l = 0; l < LN::N; ++l) {
+        const uint32_t e00 = (uint32_t)jz[l] * slice + ((uint32_t)jy[l] * pitch + (uint32_t)jx[l]);
+        const uint32_t e10 = e00 + pitch, e01 = e00 + slice, e11 = e01 + pitch;
+        if (PAIRS) {
+            const typename PairWord<T>::type* pv = reinterpret_cast<const typename PairWord<T>::type*>(vol);
+            f.raw[l].w[0] = __ldg(pv + e00); f.raw[l].w[1] = __ldg(pv + e10);
+            f.raw[l].w[2] = __ldg(pv + e01); f.raw[l].w[3] = __ldg(pv + e11);
+        } else {
+            f.raw[l].w[0] = __ldg(vol + e00); f.raw[l].w[1] = __ldg(vol + e00 + 1);
+            f.raw[l].w[2] = __ldg(vol + e10); f.raw[l].w[3] = __ldg(vol + e10 + 1);
+            f.raw[l].w[4] = __ldg(vol + e01); f.raw[l].w[5] = __ldg(vol + e01 + 1);
+            f.raw[l].w[6] = __ldg(vol + e11); f.raw[l].w[7] = __ldg(vol + e11 + 1);
+        }
+    }
+}
+
+// loaded texels + weights -> interpolated sample (same arithmetic as sample_lanes)
+template <typename T, int FM, bool PAIRS, typename L>
+__device__ __forceinline__ L finish_fetch(const Fetch<T, FM, PAIRS, L>& f)
+{
+    typedef Lanes<L> LN;
+    float b[2][8];
+#pragma unroll
+    for (int l = 0; l < LN::N; ++l) {
+        if (PAIRS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) unpack_biased<T>((typename PairWord<T>::type)f.raw[l].w[k], b[l][2 * k], b[l][2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b[l][k] = __uint_as_float(0x4B000000u | f.raw[l].w[k]);
+        }
+    }
+    L v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = LN::map([&](int l) { return b[l][k]; });
+    const L B = LN::splat(8388608.0f);
+    const L c00 = ffma(f.wx, fsub(v[1], v[0]), fsub(v[0], B));
+    const L c10 = ffma(f.wx, fsub(v[3], v[2]), fsub(v[2], B));
+    const L c01 = ffma(f.wx, fsub(v[5], v[4]), fsub(v[4], B));
+    const L c11 = ffma(f.wx, fsub(v[7], v[6]), fsub(v[6], B));
+    const L c0 = ffma(f.wy, fsub(c10, c00), c00);
+    const L c1 = ffma(f.wy, fsub(c11, c01), c01);
+    return ffma(f.wz, fsub(c1, c0), c0);
+}
+
+// Same contract as march_lanes (trilinear): `pos` is the position of the next sample to take on
+// entry and on exit; returns the `done` bits.
+template <typename T, int TCDIV, int WIN, int FM, typename L, bool PAIRS>
+__device__ __forceinline__ unsigned march_lanes_pipe(const FrameConsts& fc, const T* __restrict__ vol, uint32_t pitch,
+                                                     uint32_t slice, L pos[3], const L dstep[3], L& C, L& A, int& iter)
+{
+    typedef Lanes<L> LN;
+    const L half0 = LN::splat(fc.half_len[0]), half1 = LN::splat(fc.half_len[1]), half2 = LN::splat(fc.half_len[2]);
+    const L one = LN::splat(1.0f);
+    const L alpha = LN::splat(fc.alpha_scale);
+    const L vfmin = LN::splat(fc.fmin);
+    auto coords = [&](const L p[3], L& tx, L& ty, L& tz) -> unsigned {          // :175-192 + the box part of :118
+        tx = div_by_l<TCDIV>(fadd(p[0], half0), fc.denom[0], fc.inv_denom[0]);
+        ty = div_by_l<TCDIV>(fadd(p[1], half1), fc.denom[1], fc.inv_denom[1]);
+        tz = fsub_after_mul(one, div_by_l<TCDIV>(fadd(p[2], half2), fc.denom[2], fc.inv_denom[2]));
+        unsigned out = 0;
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) {
+            const unsigned m = max(max(__float_as_uint(LN::get(tx, l)), __float_as_uint(LN::get(ty, l))), __float_as_uint(LN::get(tz, l)));
+            if (m > 0x3F800000u) out |= 1u << l;
+        }
+        return out;
+    };
+    auto opaque = [&]() -> unsigned {                                            // the opacity part of :118
+        unsigned o = 0;
+#pragma unroll
+        for (int l = 0; l < LN::N; ++l) if (__float_as_uint(LN::get(A, l)) >= 0x3F733333u) o |= 1u << l;
+        return o;
+    };
+
+    L tx, ty, tz;
+    unsigned done = coords(pos, tx, ty, tz) | opaque();
+    if (done || iter >= 10000) return done;
+    Fetch<T, FM, PAIRS, L> cur;
+    issue_fetch<T, FM, PAIRS, L>(vol, pitch, slice, fc.dimf, tx, ty, tz, cur);
+    for (;;) {
+        // stage A for the next sample: position, box test, addresses, loads
+        L npos[3] = {fadd(pos[0], dstep[0]), fadd(pos[1], dstep[1]), fadd(pos[2], dstep[2])};     // :136
+        const unsigned out_next = coords(npos, tx, ty, tz);
+        Fetch<T, FM, PAIRS, L> nxt;
+        if (!out_next) issue_fetch<T, FM, PAIRS, L>(vol, pitch, slice, fc.dimf, tx, ty, tz, nxt);
+        // stage B for the pending sample: interpolate, window, composite
+        const L s = finish_fetch<T, FM, PAIRS, L>(cur);
+        L v;
+        if (WIN == WIN_COVERS0) {
+            v = div_by_l<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        } else {
+            const L cl = LN::map([&](int l) { return fminf(fmaxf(LN::get(s, l), fc.fmin), fc.fmax); });
+            v = div_by_l<DIV_MARKSTEIN>(fsub(cl, vfmin), fc.frange, fc.inv_frange);
+        }
+        const L a = fmul(v, alpha);                                              // :130-132
+        const L c = fmul(v, a);
+        const L t = fsub(one, A);
+        C = fadd_after_mul(C, fmul(c, t));
+        A = fadd_after_mul(A, fmul(a, t));
+        ++iter;
+        pos[0] = npos[0]; pos[1] = npos[1]; pos[2] = npos[2];
+        done = out_next | opaque();
+        if (done || iter >= 10000) break;
+        cur = nxt;
+    }
+    return done;
+}
+
+// ------------------------------------------------------------------------------------------
+// One ray per thread with f32x2 packing INSIDE the ray: the x/y components of position, texture
+// coordinate, texel coordinate and weights travel as one packed pair, the four x-lerps run as
+// two packed lerps over the (z, z+1) row pairs, the two y-lerps as one, and c*t / a*t as one
+// packed multiply.  ~14 fewer issue slots per sample than the scalar loop at the same register
+// count and occupancy.  Same operation sequence per value as march_lanes -> identical bits.
+// UNIT: every tex-coord divisor is exactly 1 (cubic volume, unit spacing): q/1 = q, no multiply.
+// NOCAP: the host proved the 10000-iteration cap of VolumeRenderer.cs:115 cannot be reached.
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ void march_ray_packed(const FrameConsts& fc, const T* __restrict__ vol, uint32_t pitch, uint32_t slice,
+                                                 const float pos0[3], const float dstep[3], float& outC, float& outA)
+{
+    f2 pxy = mk2(pos0[0], pos0[1]);
+    float pz = pos0[2];
+    const f2 dxy = mk2(dstep[0], dstep[1]);
+    const float dz = dstep[2];
+    const f2 hxy = mk2(fc.half_len[0], fc.half_len[1]);
+    const float hz = fc.half_len[2];
+    const f2 ixy = mk2(fc.inv_denom[0], fc.inv_denom[1]);
+    const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
+    const float nz = fc.dimf[2];
+    const f2 mhalf = splat2(-0.5f), B2 = splat2(8388608.0f);
+    const T* __restrict__ volp = vol + ((size_t)slice + pitch + 1);
+    float C = 0.0f, A = 0.0f;
+    for (int iter = 0; NOCAP || iter < 10000; ++iter) {
+        // cartesianToTextureCoord :175-192
+        const f2 qxy = fadd(pxy, hxy);
+        const float qz = __fadd_rn(pz, hz);
+        f2 txy;
+        float tzq;
+        if (UNIT) { txy = qxy; tzq = qz; }
+        else if (TCDIV == DIV_RECIP_EXACT) { txy = fmul(qxy, ixy); tzq = __fmul_rn(qz, fc.inv_denom[2]); }
+        else {
+            const f2 q0 = fmul(qxy, ixy);
+            const f2 r = ffma(mk2(-fc.denom[0], -fc.denom[1]), q0, qxy);
+            txy = ffma(r, ixy, q0);
+            tzq = div_by<DIV_MARKSTEIN>(qz, fc.denom[2], fc.inv_denom[2]);
+        }
+        const float tz = __fsub_rn(1.0f, tzq);
+        const unsigned m = max(max(__float_as_uint(lo(txy)), __float_as_uint(hi(txy))), __float_as_uint(tz));
+        if (m > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) break;           // :118
+        // texel coordinates, indices, weights
+        const f2 fxy = ffma(txy, nxy, mhalf);
+        const float fz = __fmaf_rn(tz, nz, -0.5f);
+        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
+        const f2 wxy = fsub(fxy, mk2((float)ix, (float)iy));
+        const float wz = __fsub_rn(fz, (float)iz);
+        // texel (ix+1, iy+1, iz+1) of the padded volume; the +1s live in `volp` (signed 32-bit index:
+        // the host selects this kernel only below 2^31 padded voxels)
+        const int e00 = iz * (int)slice + (iy * (int)pitch + ix);
+        const int e10 = e00 + (int)pitch, e01 = e00 + (int)slice, e11 = e01 + (int)pitch;
+        // biased texels 2^23 + v, paired over (z, z+1): A = rows (y,z),(y,z+1); B = rows (y+1,z),(y+1,z+1)
+        const f2 loA = mk2(__uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e00)),     __uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e01)));
+        const f2 hiA = mk2(__uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e00 + 1)), __uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e01 + 1)));
+        const f2 loB = mk2(__uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e10)),     __uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e11)));
+        const f2 hiB = mk2(__uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e10 + 1)), __uint_as_float(0x4B000000u | (uint32_t)__ldg(volp + e11 + 1)));
+        const f2 wxx = splat2(lo(wxy)), wyy = splat2(hi(wxy));
+        const f2 cA = ffma(wxx, fsub(hiA, loA), fsub(loA, B2));        // (c00, c01)
+        const f2 cB = ffma(wxx, fsub(hiB, loB), fsub(loB, B2));        // (c10, c11)
+        const f2 cy = ffma(wyy, fsub(cB, cA), cA);                     // (c0, c1)
+        const float s = __fmaf_rn(wz, __fsub_rn(hi(cy), lo(cy)), lo(cy));
+        // :122-124
+        float v;
+        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
+        // :130-132
+        const float a = __fmul_rn(v, fc.alpha_scale);
+        const float c = __fmul_rn(v, a);
+        const float t = __fsub_rn(1.0f, A);
+        const f2 ca_t = fmul(mk2(c, a), splat2(t));
+        C = __fadd_rn(C, lo(ca_t));
+        A = __fadd_rn(A, hi(ca_t));
+        pxy = fadd(pxy, dxy);                                          // :136
+        pz = __fadd_rn(pz, dz);
+    }
+    outC = C; outA = A;
+}
+
+// launch bounds measured on the headline frame: the capless loop fits 32 registers (8 CTAs/SM,
+// 3.50 ms); with the iteration counter 32 registers spill (4.31 ms) and 40 are best (3.78 ms)
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__global__ void __launch_bounds__(256, NOCAP ? 8 : 6)
+march_packed_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ FastArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const RaySetup r = setup_ray(fc, px, py);
+    float C = 0.0f, A = 0.0f;
+    if (r.hit) {
+        float pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
+            ds[i] = __fmul_rn(r.dir[i], fc.step);
+        }
+        march_ray_packed<T, TCDIV, WIN, UNIT, NOCAP>(fc, static_cast<const T*>(args.vol), args.pitch, args.slice_lo, pos, ds, C, A);
+    }
+    const int orow = fc.compact ? lrow : py;
+    reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
+}
+
 constexpr int FAST_THREADS = 256;
 
 // RAYS = 2: a thread owns pixels (2i, 2i+1) of a row; a warp covers 16x4 pixels, a CTA 64x8.
 // RAYS = 1: a warp covers 8x4 pixels, a CTA 32x8 (same as the baseline kernel).
-template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS>
-__global__ void __launch_bounds__(FAST_THREADS)
-march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ FastArgs args)
+// (forcing 32 registers/thread with __launch_bounds__(256, 8) spills and is slower: 4.24 ms vs 3.97 ms)
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS, bool PAIRS, bool PIPE>
+__device__ __forceinline__ void fast_tile(const FrameConsts& fc, const FastArgs& args, int bx, int by, int warp)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);       // thread column
-    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int lane = threadIdx.x & 31;
+    const int tx = bx * 32 + (warp & 3) * 8 + (lane & 7);       // thread column
+    const int lrow = by * 8 + (warp >> 2) * 4 + (lane >> 3);
     const int px0 = tx * RAYS;
     if (px0 >= fc.W || lrow >= args.local_rows) return;
     const int py = owned_row_to_global(fc, lrow);
@@ -254,7 +532,8 @@ march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant_
                 ds[i].v = __fmul_rn(r.dir[i], fc.step);
             }
             int iter = 0;
-            march_lanes<T, FILTER, TCDIV, WIN, FM, f1>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+            if (PIPE && FILTER == VR_FILTER_TRILINEAR) march_lanes_pipe<T, TCDIV, WIN, FM, f1, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+            else march_lanes<T, FILTER, TCDIV, WIN, FM, f1, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter);
         }
         out[px0] = make_float4(C.v, C.v, C.v, A.v);
         return;
@@ -280,7 +559,9 @@ march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 3; ++i) { pos[i] = mk2(p0[i], p1[i]); ds[i] = mk2(d0[i], d1[i]); }
         f2 C = mk2(0.f, 0.f), A = mk2(0.f, 0.f);
-        const unsigned done = march_lanes<T, FILTER, TCDIV, WIN, FM, f2>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        const unsigned done = (PIPE && FILTER == VR_FILTER_TRILINEAR)
+            ? march_lanes_pipe<T, TCDIV, WIN, FM, f2, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter)
+            : march_lanes<T, FILTER, TCDIV, WIN, FM, f2, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter);
         C0 = lo(C); C1 = hi(C); A0 = lo(A); A1 = hi(A);
 #pragma unroll
         for (int i = 0; i < 3; ++i) { p0[i] = lo(pos[i]); p1[i] = hi(pos[i]); }
@@ -293,11 +574,23 @@ march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 3; ++i) { pos[i].v = second ? p1[i] : p0[i]; ds[i].v = second ? d1[i] : d0[i]; }
         f1 C{second ? C1 : C0}, A{second ? A1 : A0};
-        march_lanes<T, FILTER, TCDIV, WIN, FM, f1>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        if (PIPE && FILTER == VR_FILTER_TRILINEAR) march_lanes_pipe<T, TCDIV, WIN, FM, f1, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter);
+        else march_lanes<T, FILTER, TCDIV, WIN, FM, f1, PAIRS>(fc, vol, pitch, slice, pos, ds, C, A, iter);
         if (second) { C1 = C.v; A1 = A.v; } else { C0 = C.v; A0 = A.v; }
     }
     out[px0] = make_float4(C0, C0, C0, A0);
     if (have1) out[px0 + 1] = make_float4(C1, C1, C1, A1);
+}
+
+// One CTA per 32x8 (64x8 with two rays per thread) pixel tile.  Measured alternatives that did
+// not pay (tools/marchlab, profiles/r01/experiments.md): persistent CTAs pulling tiles from an
+// atomic counter (4.46 ms vs 3.99 ms), persistent WARPS pulling 8x4 patches (4.10 ms; 0.85 vs
+// 0.89 ms on a 1/8 partition), long-rays-first tile order (no change).
+template <typename T, int FILTER, int TCDIV, int WIN, int FM, int RAYS, bool PAIRS = false, bool PIPE = false>
+__global__ void __launch_bounds__(FAST_THREADS)
+march_fast_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ FastArgs args)
+{
+    fast_tile<T, FILTER, TCDIV, WIN, FM, RAYS, PAIRS, PIPE>(fc, args, blockIdx.x, blockIdx.y, threadIdx.x >> 5);
 }
 
 }  // namespace vr

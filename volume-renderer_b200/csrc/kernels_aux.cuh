@@ -31,6 +31,24 @@ __global__ void pad_volume_kernel(const T* __restrict__ src, T* __restrict__ dst
     }
 }
 
+// ---- ingest: pair-packed variant of the padded volume: word x = (voxel x, voxel x+1) ------------
+template <typename T, typename W>
+__global__ void pad_pairs_kernel(const T* __restrict__ src, W* __restrict__ dst, int nx, int ny, int nz, uint32_t pitch)
+{
+    const uint64_t rows = (uint64_t)(ny + 2) * (uint64_t)(nz + 2);
+    for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int jz = (int)(row / (uint64_t)(ny + 2));
+        const int jy = (int)(row - (uint64_t)jz * (uint64_t)(ny + 2));
+        const int y = min(max(jy - 1, 0), ny - 1), z = min(max(jz - 1, 0), nz - 1);
+        const T* s = src + ((uint64_t)z * ny + y) * (uint64_t)nx;
+        W* d = dst + row * (uint64_t)pitch;
+        for (uint32_t jx = threadIdx.x; jx < pitch; jx += blockDim.x) {
+            const int x0 = min(max((int)jx - 1, 0), nx - 1), x1 = min(max((int)jx, 0), nx - 1);
+            d[jx] = (W)((W)s[x0] | ((W)s[x1] << (8 * sizeof(T))));
+        }
+    }
+}
+
 // ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
 template <typename T>
 __global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)

@@ -204,6 +204,18 @@ int launch_direct(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStrea
                        : launch_direct_t<uint16_t, false>(c, plan, args, s);
 }
 
+template <typename T, int WIN>
+void launch_packed_tw(const vr::FrameConsts& fc, const vr::FastArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_packed_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_packed_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_packed_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_packed_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else                      march_packed_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+}
+
 template <typename T>
 int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
@@ -213,6 +225,20 @@ int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStrea
     const dim3 block(FAST_THREADS), grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
     const FrameConsts& fc = plan.fc;
     const bool tri = fc.filter == VR_FILTER_TRILINEAR, recip = plan.tcdiv == DIV_RECIP_EXACT, cov = win == WIN_COVERS0;
+    const uint64_t padded_voxels = c->slice * (uint64_t)(c->dim[2] + 2);
+    if (tri && padded_voxels < (1ull << 31)) {
+        // trilinear: one ray per thread, f32x2 packing inside the ray (signed 32-bit texel indices)
+        const bool unit = recip && fc.denom[0] == 1.0f && fc.denom[1] == 1.0f && fc.denom[2] == 1.0f;
+        // VolumeRenderer.cs:115 caps the loop at 10000 iterations; a ray cannot take more than
+        // |box diagonal| / step + 2 = |vol_size| / step_scale + 2 samples
+        const double nmax = std::sqrt((double)c->dim[0] * c->dim[0] + (double)c->dim[1] * c->dim[1] + (double)c->dim[2] * c->dim[2]) /
+                            (double)fc.step_scale + 4.0;
+        const bool nocap = nmax < 10000.0;
+        if (cov) launch_packed_tw<T, WIN_COVERS0>(fc, a, grid, s, unit, recip, nocap);
+        else     launch_packed_tw<T, WIN_CLAMP>(fc, a, grid, s, unit, recip, nocap);
+        VR_CUDA(cudaGetLastError());
+        return VR_OK;
+    }
 #define VR_FAST(F, D, W) march_fast_kernel<T, F, D, W, FLOOR_XU1, 1><<<grid, block, 0, s>>>(fc, a)
     if (tri) {
         if (recip) { if (cov) VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_COVERS0); else VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_CLAMP); }
