@@ -49,9 +49,11 @@ enum { VR_FILTER_NEAREST = 0, VR_FILTER_TRILINEAR = 1 };
  *   DIRECT   one thread per ray, texels straight from HBM through L1/L2; handles every mode
  *   FAST     same data path, issue-slot-optimised loop (DVR, default view, no TF)
  *   WINDOWED persistent screen-tile CTAs marching through TMA-staged shared-memory windows
+ *   TEXGATHER trilinear only: the 2x2 texel footprint of each slice fetched with one exact
+ *            texture-gather (tld4) from a layered CUDA array; interpolation stays in fp32 ALU
  *   AUTO     the fastest kernel that covers the frame's parameters
- * A request the frame's parameters do not allow falls back to DIRECT. */
-enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2, VR_KERNEL_FAST = 3 };
+ * A request the frame's parameters do not allow falls back (TEXGATHER/WINDOWED -> FAST -> DIRECT). */
+enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2, VR_KERNEL_FAST = 3, VR_KERNEL_TEXGATHER = 4 };
 
 typedef struct vr_context vr_context;
 

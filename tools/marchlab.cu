@@ -33,6 +33,7 @@ struct Lab {
     int rows = 1080;          // local rows rendered (emulated rank of a partition)
     uint16_t* d_pad = nullptr; uint32_t pitch = 0; uint64_t slice = 0;
     uint32_t* d_pairs = nullptr;
+    cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0;
     float *d_ref = nullptr, *d_out = nullptr;
     FrameConsts fc;
     cudaEvent_t e0, e1;
@@ -99,6 +100,17 @@ static void run_packed(Lab& L, const char* name, double samples)
     check(L, name, ms, samples);
 }
 
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+static void run_texgather(Lab& L, const char* name, double samples)
+{
+    if (g_only && !strstr(name, g_only)) return;
+    TexArgs a{};
+    a.tex = L.tex; a.out = L.d_out; a.local_rows = L.rows;
+    dim3 grid((L.W + 31) / 32, (L.rows + 7) / 8), block(256);
+    const float ms = time_kernel(L, [&] { march_texgather_kernel<T, TCDIV, WIN, UNIT, NOCAP><<<grid, block>>>(L.fc, a); });
+    check(L, name, ms, samples);
+}
+
 template <typename T>
 static void run_windowed(Lab& L, const char* name, double samples, int tcdiv, int win, int ctas_per_sm, int sms, bool stats = false)
 {
@@ -147,6 +159,19 @@ int main(int argc, char** argv)
     L.slice = (uint64_t)L.pitch * (N + 2);
     CK(cudaMalloc(&L.d_pad, L.slice * (N + 2) * 2 + 256));
     pad_volume_kernel<uint16_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pad, N, N, N, L.pitch);
+    {   // layered 2-D array + point-sampling texture object for the gather variant
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        CK(cudaMalloc3DArray(&L.arr, &cd, make_cudaExtent(N, N, N), cudaArrayLayered));
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(d_src, (size_t)N * 2, N, N);
+        cp.dstArray = L.arr; cp.extent = make_cudaExtent(N, N, N); cp.kind = cudaMemcpyDeviceToDevice;
+        CK(cudaMemcpy3D(&cp));
+        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = L.arr;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&L.tex, &rd, &td, nullptr));
+    }
     CK(cudaMalloc(&L.d_pairs, L.slice * (N + 2) * 4 + 256));
     pad_pairs_kernel<uint16_t, uint32_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pairs, N, N, N, L.pitch);
     CK(cudaDeviceSynchronize());
@@ -192,6 +217,8 @@ int main(int argc, char** argv)
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (auto occupancy)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 0, prop.multiProcessorCount);
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (2 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 2, prop.multiProcessorCount);
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (4 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 4, prop.multiProcessorCount);
+        run_texgather<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, true>(L, "texgather packed covers0 UNIT NOCAP", samples);
+        run_texgather<uint16_t, DIV_RECIP_EXACT, WIN_CLAMP, false, false>(L, "texgather packed clamp", samples);
         run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, false, false>(L, "packed-in-ray covers0", samples);
         run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, false>(L, "packed-in-ray covers0 UNIT", samples);
         run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, true>(L, "packed-in-ray covers0 UNIT NOCAP", samples);

@@ -64,6 +64,9 @@ struct vr_context {
     int bpv = 0;
     uint32_t pitch = 0;                  // elements
     uint64_t slice = 0;                  // elements
+    // second copy for the texture-gather kernel: layered 2-D array (layer = z), point sampling
+    cudaArray_t d_arr = nullptr;
+    cudaTextureObject_t tex = 0;
     float voxel_size[3] = {1.f, 1.f, 1.f};
     vr_volume_stats stats{};
     bool have_stats = false;
@@ -216,6 +219,45 @@ void launch_packed_tw(const vr::FrameConsts& fc, const vr::FastArgs& a, dim3 gri
     else                      march_packed_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
 }
 
+template <typename T, int WIN>
+void launch_tex_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texgather_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texgather_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+}
+
+// loop-shape flags shared by the packed kernels
+void packed_flags(const vr_context* c, const LaunchPlan& plan, bool* unit, bool* recip, bool* nocap)
+{
+    const vr::FrameConsts& fc = plan.fc;
+    *recip = plan.tcdiv == vr::DIV_RECIP_EXACT;
+    *unit = *recip && fc.denom[0] == 1.0f && fc.denom[1] == 1.0f && fc.denom[2] == 1.0f;
+    // VolumeRenderer.cs:115 caps the loop at 10000 iterations; a ray cannot take more than
+    // |box diagonal| / step + 2 = |vol_size| / step_scale + 2 samples
+    const double nmax = std::sqrt((double)c->dim[0] * c->dim[0] + (double)c->dim[1] * c->dim[1] + (double)c->dim[2] * c->dim[2]) /
+                        (double)fc.step_scale + 4.0;
+    *nocap = nmax < 10000.0;
+}
+
+int launch_texgather(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    vr::TexArgs a{};
+    a.tex = c->tex; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
+    bool unit, recip, nocap;
+    packed_flags(c, plan, &unit, &recip, &nocap);
+    // the element type only matters for the array's channel format; uint16_t instantiation serves both
+    if (win == vr::WIN_COVERS0) launch_tex_tw<uint16_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
+    else                        launch_tex_tw<uint16_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
 template <typename T>
 int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
@@ -228,12 +270,8 @@ int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStrea
     const uint64_t padded_voxels = c->slice * (uint64_t)(c->dim[2] + 2);
     if (tri && padded_voxels < (1ull << 31)) {
         // trilinear: one ray per thread, f32x2 packing inside the ray (signed 32-bit texel indices)
-        const bool unit = recip && fc.denom[0] == 1.0f && fc.denom[1] == 1.0f && fc.denom[2] == 1.0f;
-        // VolumeRenderer.cs:115 caps the loop at 10000 iterations; a ray cannot take more than
-        // |box diagonal| / step + 2 = |vol_size| / step_scale + 2 samples
-        const double nmax = std::sqrt((double)c->dim[0] * c->dim[0] + (double)c->dim[1] * c->dim[1] + (double)c->dim[2] * c->dim[2]) /
-                            (double)fc.step_scale + 4.0;
-        const bool nocap = nmax < 10000.0;
+        bool unit, recip2, nocap;
+        packed_flags(c, plan, &unit, &recip2, &nocap);
         if (cov) launch_packed_tw<T, WIN_COVERS0>(fc, a, grid, s, unit, recip, nocap);
         else     launch_packed_tw<T, WIN_CLAMP>(fc, a, grid, s, unit, recip, nocap);
         VR_CUDA(cudaGetLastError());
@@ -266,8 +304,10 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool windowed_ok = fast_ok && vr::windowed_supported(fc, c->bpv, padded_voxels);
     const int win = (c->params.min_val == 0 && c->have_stats && c->stats.max_value <= c->params.max_val)
                         ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
+    const bool tex_ok = fast_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;
     int want = c->params.kernel;
-    if (want == VR_KERNEL_AUTO) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_AUTO) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
+    if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
     if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
     if (want == VR_KERNEL_FAST && !fast_ok) want = VR_KERNEL_DIRECT;
     *launches = 1;
@@ -279,6 +319,10 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
         // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
         cudaGetLastError();
         want = VR_KERNEL_FAST;
+    }
+    if (want == VR_KERNEL_TEXGATHER) {
+        *used = VR_KERNEL_TEXGATHER;
+        return launch_texgather(c, plan, d_out, s, win);
     }
     if (want == VR_KERNEL_FAST) {
         *used = VR_KERNEL_FAST;
@@ -344,6 +388,30 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
     VR_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_mm); cudaFree(d_bins);
 
+    // layered array for the gather kernel (limits of layered 2-D arrays: 32768 x 32768 x 2048)
+    if (c->tex) { cudaDestroyTextureObject(c->tex); c->tex = 0; }
+    if (c->d_arr) { cudaFreeArray(c->d_arr); c->d_arr = nullptr; }
+    if (nz <= 2048 && nx <= 32768 && ny <= 32768) {
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(T), 0, 0, 0, cudaChannelFormatKindUnsigned);
+        cudaArray_t arr = nullptr;
+        if (cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz), cudaArrayLayered) == cudaSuccess) {
+            cudaMemcpy3DParms cp = {};
+            cp.srcPtr = make_cudaPitchedPtr(const_cast<T*>(d_src), (size_t)nx * sizeof(T), nx, ny);
+            cp.dstArray = arr; cp.extent = make_cudaExtent(nx, ny, nz); cp.kind = cudaMemcpyDeviceToDevice;
+            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+            cudaTextureObject_t tex = 0;
+            if (cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+                cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess) {
+                c->d_arr = arr; c->tex = tex;
+            } else {
+                cudaFreeArray(arr);
+            }
+        }
+        cudaGetLastError();     // without the array the LDG kernels serve every frame
+    }
     if (c->d_vol) cudaFree(c->d_vol);
     c->d_vol = d_new; c->vol_bytes = bytes;
     c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
@@ -440,6 +508,8 @@ void vr_destroy(vr_context* c)
     if (!c) return;
     cudaSetDevice(c->device);
     vr::windowed_release(c->win);
+    if (c->tex) cudaDestroyTextureObject(c->tex);
+    if (c->d_arr) cudaFreeArray(c->d_arr);
     if (c->d_vol) cudaFree(c->d_vol);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_rgb8) cudaFree(c->d_rgb8);
@@ -541,7 +611,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_FAST)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXGATHER)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         VR_CUDA(cudaSetDevice(c->device));
