@@ -569,8 +569,10 @@ __global__ void __launch_bounds__(256, NOCAP ? 8 : 6)
 march_texgather_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    // (mapping each 4-lane quad to a 2x2 pixel block was measured: no change on K2, +-3 % on K0/K1)
+    const int qx = lane & 7, qy = lane >> 3;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + qx;
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + qy;
     if (px >= fc.W || lrow >= args.local_rows) return;
     const int py = owned_row_to_global(fc, lrow);
     if (py >= fc.H) return;
