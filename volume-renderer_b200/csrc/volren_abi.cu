@@ -299,12 +299,12 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     // the optimised kernels cover: DVR, default view, no TF, ordered window with a verified
     // Markstein divisor, alpha_scale >= 0 (range tests on bit patterns), 32-bit texel indices,
     // correctly rounded tex-coord division without div.rn
-    const bool fast_ok = !plan.generic && plan.tcdiv != vr::DIV_IEEE && c->params.alpha_scale >= 0.0f &&
-                         padded_voxels < (1ull << 32);
+    const bool base_ok = !plan.generic && plan.tcdiv != vr::DIV_IEEE && c->params.alpha_scale >= 0.0f;
+    const bool fast_ok = base_ok && padded_voxels < (1ull << 32);          // LSU kernels: 32-bit texel indices
     const bool windowed_ok = fast_ok && vr::windowed_supported(fc, c->bpv, padded_voxels);
     const int win = (c->params.min_val == 0 && c->have_stats && c->stats.max_value <= c->params.max_val)
                         ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
-    const bool tex_ok = fast_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;
+    const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     int want = c->params.kernel;
     if (want == VR_KERNEL_AUTO) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
