@@ -153,6 +153,16 @@ VR_API int vr_render_device(vr_context* ctx, float* d_rgba, int compact, void* c
 VR_API int vr_assemble_tiles(vr_context* ctx, const float* d_gathered, float* d_frame,
                              int world, int tile_rows, void* cuda_stream);
 
+/* ---- fused multi-GPU hand-off over NVLink peer memory (no reference counterpart): rank 0
+ *      exports its frame buffer, every other rank (one process per GPU) maps it and renders
+ *      its row tiles STRAIGHT into it -- vr_render_device(ctx, peer_frame, 0, ...) -- so the
+ *      only per-frame collective left is a barrier.  The 64-byte handle is a cudaIpcMemHandle_t;
+ *      ship it to the other processes any way you like (bench.py broadcasts it with NCCL). ---- */
+VR_API int vr_frame_device_ptr(vr_context* ctx, float** d_frame);
+VR_API int vr_frame_export_ipc(vr_context* ctx, unsigned char handle[64]);
+VR_API int vr_frame_open_ipc(vr_context* ctx, const unsigned char handle[64], float** d_peer_frame);
+VR_API int vr_frame_close_ipc(vr_context* ctx, float* d_peer_frame);
+
 /* ---- display/save step after the path: float RGBA -> RGB8 (clamp, no gamma), vertical
  *      flip; replaces glBlitFramebuffer/glReadPixels, RendererCore.cpp:158-171 ---- */
 VR_API int vr_read_rgb8(vr_context* ctx, uint8_t* host_rgb, int flip_vertical);

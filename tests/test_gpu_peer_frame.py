@@ -1,0 +1,67 @@
+"""-m gpu: the fused multi-GPU hand-off -- rank 1 maps rank 0's frame through CUDA IPC and its
+march kernel stores its row tiles straight into it.  Two real processes; both use cuda:0 when
+the box has a single GPU (the IPC mapping path is the same), cuda:rank otherwise."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import volren_b200 as vb
+    import scenarios
+    dev = rank if torch.cuda.device_count() >= world else 0
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    W, H, tile_rows = 200, 150, 16
+    kw = dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)
+    with vb.Context(W, H, device=dev) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(cam)
+        ctx.set_params(vb.default_params(**kw))
+        full = None
+        if rank == 0:
+            full, _ = ctx.render()                                   # unpartitioned frame, for comparison
+            # overwrite rank 0's frame with a different image so rows nobody stores would be noticed
+            ctx.set_params(vb.default_params(alpha_scale=0.9, min_val=50, max_val=200, filter=0))
+            poison, _ = ctx.render()
+            assert not np.array_equal(poison, full)
+            ctx.set_params(vb.default_params(**kw))
+        handle = [ctx.frame_export_ipc() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        ptr = ctx.frame_device_ptr() if rank == 0 else ctx.frame_open_ipc(handle[0])
+        ctx.set_partition(rank, world, tile_rows)
+        dist.barrier()
+        st = ctx.render_device(ptr, compact=False)
+        assert st.kernel_launches >= 1
+        dist.barrier()                                               # every rank's stores have landed
+        if rank == 0:
+            got = ctx.read_frame()
+            np.save(out_path, np.array([1 if np.array_equal(got.view(np.uint32), full.view(np.uint32)) else 0]))
+        dist.barrier()
+        if rank != 0:
+            ctx.frame_close_ipc(ptr)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_stores_assemble_the_frame_in_rank0(tmp_path, world):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert np.load(out)[0] == 1

@@ -34,6 +34,7 @@ struct Lab {
     uint16_t* d_pad = nullptr; uint32_t pitch = 0; uint64_t slice = 0;
     uint32_t* d_pairs = nullptr;
     cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0;
+    cudaArray_t arrf = nullptr; cudaTextureObject_t texf = 0;
     float *d_ref = nullptr, *d_out = nullptr;
     FrameConsts fc;
     cudaEvent_t e0, e1;
@@ -100,14 +101,19 @@ static void run_packed(Lab& L, const char* name, double samples)
     check(L, name, ms, samples);
 }
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__global__ void u16_to_f32_kernel(const uint16_t* __restrict__ s, float* __restrict__ d, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = (float)s[i];
+}
+
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, bool FLOATTEX = false>
 static void run_texgather(Lab& L, const char* name, double samples)
 {
     if (g_only && !strstr(name, g_only)) return;
     TexArgs a{};
-    a.tex = L.tex; a.out = L.d_out; a.local_rows = L.rows;
+    a.tex = FLOATTEX ? L.texf : L.tex; a.out = L.d_out; a.local_rows = L.rows;
     dim3 grid((L.W + 31) / 32, (L.rows + 7) / 8), block(256);
-    const float ms = time_kernel(L, [&] { march_texgather_kernel<T, TCDIV, WIN, UNIT, NOCAP><<<grid, block>>>(L.fc, a); });
+    const float ms = time_kernel(L, [&] { march_texgather_kernel<T, TCDIV, WIN, UNIT, NOCAP, FLOATTEX><<<grid, block>>>(L.fc, a); });
     check(L, name, ms, samples);
 }
 
@@ -172,6 +178,22 @@ int main(int argc, char** argv)
         td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
         CK(cudaCreateTextureObject(&L.tex, &rd, &td, nullptr));
     }
+    {   // float-texel layered array (lab experiment)
+        float* d_f; CK(cudaMalloc(&d_f, nvox * 4));
+        u16_to_f32_kernel<<<prop.multiProcessorCount * 16, 256>>>(d_src, d_f, nvox);
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        CK(cudaMalloc3DArray(&L.arrf, &cd, make_cudaExtent(N, N, N), cudaArrayLayered));
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(d_f, (size_t)N * 4, N, N);
+        cp.dstArray = L.arrf; cp.extent = make_cudaExtent(N, N, N); cp.kind = cudaMemcpyDeviceToDevice;
+        CK(cudaMemcpy3D(&cp));
+        CK(cudaFree(d_f));
+        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = L.arrf;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&L.texf, &rd, &td, nullptr));
+    }
     CK(cudaMalloc(&L.d_pairs, L.slice * (N + 2) * 4 + 256));
     pad_pairs_kernel<uint16_t, uint32_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pairs, N, N, N, L.pitch);
     CK(cudaDeviceSynchronize());
@@ -218,6 +240,7 @@ int main(int argc, char** argv)
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (2 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 2, prop.multiProcessorCount);
         run_windowed<uint16_t>(L, "windowed TMA 1ray covers0 (4 CTA/SM)", samples, DIV_RECIP_EXACT, WIN_COVERS0, 4, prop.multiProcessorCount);
         run_texgather<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, true>(L, "texgather packed covers0 UNIT NOCAP", samples);
+        run_texgather<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, true, true>(L, "texgather FLOAT texels covers0 UNIT NOCAP", samples);
         run_texgather<uint16_t, DIV_RECIP_EXACT, WIN_CLAMP, false, false>(L, "texgather packed clamp", samples);
         run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, false, false>(L, "packed-in-ray covers0", samples);
         run_packed<uint16_t, DIV_RECIP_EXACT, WIN_COVERS0, true, false>(L, "packed-in-ray covers0 UNIT", samples);

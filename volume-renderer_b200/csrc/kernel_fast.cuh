@@ -491,7 +491,17 @@ __device__ __forceinline__ void tld4_layer(cudaTextureObject_t tex, int layer, f
                  : "l"(tex), "r"(layer), "f"(x), "f"(y));
 }
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ void tld4_layer_f32(cudaTextureObject_t tex, int layer, float x, float y,
+                                               float& t_x0y1, float& t_x1y1, float& t_x1y0, float& t_x0y0)
+{
+    asm volatile("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                 : "=f"(t_x0y1), "=f"(t_x1y1), "=f"(t_x1y0), "=f"(t_x0y0)
+                 : "l"(tex), "r"(layer), "f"(x), "f"(y));
+}
+
+// FLOATTEX (lab experiment): the array holds float(v) texels, so the gather returns exact floats and
+// the 8 exponent-bias conversions + 4 un-bias subtractions disappear (at 2x array bytes)
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, bool FLOATTEX = false>
 __device__ __forceinline__ void march_ray_texgather(const FrameConsts& fc, cudaTextureObject_t tex,
                                                     const float pos0[3], const float dstep[3], float& outC, float& outA)
 {
@@ -530,17 +540,27 @@ __device__ __forceinline__ void march_ray_texgather(const FrameConsts& fc, cudaT
         const f2 wxy = fsub(fxy, flxy);
         const float wz = __fsub_rn(fz, (float)iz);
         const f2 cxy = fadd(flxy, one2);                               // corner shared by the 2x2 footprint
-        uint32_t a01, a11, a10, a00, b01, b11, b10, b00;               // slice z (a) and z+1 (b); suffix = x,y offsets
-        tld4_layer(tex, max(iz, 0), lo(cxy), hi(cxy), a01, a11, a10, a00);
-        tld4_layer(tex, min(iz + 1, zmax), lo(cxy), hi(cxy), b01, b11, b10, b00);
-        // pairs over (z, z+1): A = row y, B = row y+1
-        const f2 loA = mk2(__uint_as_float(0x4B000000u | a00), __uint_as_float(0x4B000000u | b00));
-        const f2 hiA = mk2(__uint_as_float(0x4B000000u | a10), __uint_as_float(0x4B000000u | b10));
-        const f2 loB = mk2(__uint_as_float(0x4B000000u | a01), __uint_as_float(0x4B000000u | b01));
-        const f2 hiB = mk2(__uint_as_float(0x4B000000u | a11), __uint_as_float(0x4B000000u | b11));
         const f2 wxx = splat2(lo(wxy)), wyy = splat2(hi(wxy));
-        const f2 cA = ffma(wxx, fsub(hiA, loA), fsub(loA, B2));
-        const f2 cB = ffma(wxx, fsub(hiB, loB), fsub(loB, B2));
+        f2 cA, cB;
+        if (FLOATTEX) {
+            float a01, a11, a10, a00, b01, b11, b10, b00;
+            tld4_layer_f32(tex, max(iz, 0), lo(cxy), hi(cxy), a01, a11, a10, a00);
+            tld4_layer_f32(tex, min(iz + 1, zmax), lo(cxy), hi(cxy), b01, b11, b10, b00);
+            const f2 loA = mk2(a00, b00), hiA = mk2(a10, b10), loB = mk2(a01, b01), hiB = mk2(a11, b11);
+            cA = ffma(wxx, fsub(hiA, loA), loA);
+            cB = ffma(wxx, fsub(hiB, loB), loB);
+        } else {
+            uint32_t a01, a11, a10, a00, b01, b11, b10, b00;           // slice z (a) and z+1 (b); suffix = x,y offsets
+            tld4_layer(tex, max(iz, 0), lo(cxy), hi(cxy), a01, a11, a10, a00);
+            tld4_layer(tex, min(iz + 1, zmax), lo(cxy), hi(cxy), b01, b11, b10, b00);
+            // pairs over (z, z+1): A = row y, B = row y+1
+            const f2 loA = mk2(__uint_as_float(0x4B000000u | a00), __uint_as_float(0x4B000000u | b00));
+            const f2 hiA = mk2(__uint_as_float(0x4B000000u | a10), __uint_as_float(0x4B000000u | b10));
+            const f2 loB = mk2(__uint_as_float(0x4B000000u | a01), __uint_as_float(0x4B000000u | b01));
+            const f2 hiB = mk2(__uint_as_float(0x4B000000u | a11), __uint_as_float(0x4B000000u | b11));
+            cA = ffma(wxx, fsub(hiA, loA), fsub(loA, B2));
+            cB = ffma(wxx, fsub(hiB, loB), fsub(loB, B2));
+        }
         const f2 cy = ffma(wyy, fsub(cB, cA), cA);
         const float s = __fmaf_rn(wz, __fsub_rn(hi(cy), lo(cy)), lo(cy));
         float v;
@@ -564,7 +584,7 @@ struct TexArgs {
     int local_rows;
 };
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, bool FLOATTEX = false>
 __global__ void __launch_bounds__(256, NOCAP ? 8 : 6)
 march_texgather_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
 {
@@ -585,7 +605,7 @@ march_texgather_kernel(const __grid_constant__ FrameConsts fc, const __grid_cons
             pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
             ds[i] = __fmul_rn(r.dir[i], fc.step);
         }
-        march_ray_texgather<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A);
+        march_ray_texgather<T, TCDIV, WIN, UNIT, NOCAP, FLOATTEX>(fc, args.tex, pos, ds, C, A);
     }
     const int orow = fc.compact ? lrow : py;
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);

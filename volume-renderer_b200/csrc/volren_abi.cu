@@ -697,6 +697,44 @@ int vr_assemble_tiles(vr_context* c, const float* d_gathered, float* d_frame, in
     return VR_OK;
 }
 
+int vr_frame_device_ptr(vr_context* c, float** d_frame)
+{
+    if (!c || !d_frame) return fail(VR_ERR_INVALID, "vr_frame_device_ptr: null argument");
+    *d_frame = c->d_frame;
+    return VR_OK;
+}
+
+int vr_frame_export_ipc(vr_context* c, unsigned char handle[64])
+{
+    if (!c || !handle) return fail(VR_ERR_INVALID, "vr_frame_export_ipc: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    VR_CUDA(cudaIpcGetMemHandle(&h, c->d_frame));
+    std::memcpy(handle, &h, 64);
+    return VR_OK;
+}
+
+int vr_frame_open_ipc(vr_context* c, const unsigned char handle[64], float** d_peer_frame)
+{
+    if (!c || !handle || !d_peer_frame) return fail(VR_ERR_INVALID, "vr_frame_open_ipc: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    VR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_peer_frame = static_cast<float*>(p);
+    return VR_OK;
+}
+
+int vr_frame_close_ipc(vr_context* c, float* d_peer_frame)
+{
+    if (!c || !d_peer_frame) return fail(VR_ERR_INVALID, "vr_frame_close_ipc: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    VR_CUDA(cudaIpcCloseMemHandle(d_peer_frame));
+    return VR_OK;
+}
+
 int vr_read_rgb8(vr_context* c, uint8_t* host_rgb, int flip_vertical)
 {
     if (!c || !host_rgb) return fail(VR_ERR_INVALID, "vr_read_rgb8: null argument");

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "vr_upload_volume", "vr_upload_volume_device", "vr_set_voxel_size", "vr_volume_stats_get",
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
     "vr_render", "vr_read_frame", "vr_render_device", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
+    "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
     "vr_upload_synthetic", "vr_synthetic_to_host",
 ]
 
@@ -107,6 +108,10 @@ def lib():
         L.vr_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_assemble_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vr_read_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vr_frame_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.vr_frame_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
+        L.vr_frame_open_ipc.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.vr_frame_close_ipc.argtypes = [C.c_void_p, C.c_void_p]
         L.vr_count_frame.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.vr_upload_synthetic.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3), C.c_int, C.POINTER(C.c_float * 3),
                                           C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
@@ -236,6 +241,9 @@ class Context:
         _check(lib().vr_read_frame(self._h, out.ctypes.data))
         return out
 
+    def read_frame_into(self, host_ptr: int):
+        _check(lib().vr_read_frame(self._h, C.c_void_p(host_ptr)))
+
     def render_to_host_ptr(self, host_ptr: int):
         st = RenderStats()
         _check(lib().vr_render(self._h, C.c_void_p(host_ptr), C.byref(st)))
@@ -250,6 +258,26 @@ class Context:
     def assemble_tiles(self, gathered_dptr: int, frame_dptr: int, world: int, tile_rows: int, stream: int = 0):
         _check(lib().vr_assemble_tiles(self._h, C.c_void_p(gathered_dptr), C.c_void_p(frame_dptr), world, tile_rows,
                                        C.c_void_p(stream) if stream else None))
+
+    # -- fused multi-GPU hand-off (peer stores into rank 0's frame)
+    def frame_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().vr_frame_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def frame_export_ipc(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _check(lib().vr_frame_export_ipc(self._h, buf))
+        return bytes(buf)
+
+    def frame_open_ipc(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 64)(*handle)
+        p = C.c_void_p()
+        _check(lib().vr_frame_open_ipc(self._h, buf, C.byref(p)))
+        return p.value
+
+    def frame_close_ipc(self, ptr: int):
+        _check(lib().vr_frame_close_ipc(self._h, C.c_void_p(ptr)))
 
     def read_rgb8(self, flip_vertical: bool = True) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)

@@ -54,6 +54,20 @@ def gather_tiles(local_compact: torch.Tensor, gathered: torch.Tensor | None, dst
         dist.gather(local_compact, None, dst=dst)
 
 
+def open_peer_frame(ctx, dst: int = 0) -> int:
+    """Fused hand-off: returns the device pointer every rank renders its rows into -- rank dst's own
+    frame on rank dst, the CUDA-IPC mapping of that frame (NVLink peer memory) on the others.
+    The 64-byte handle travels as a CUDA tensor over the process group."""
+    rank = dist.get_rank()
+    h = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    if rank == dst:
+        h.copy_(torch.frombuffer(bytearray(ctx.frame_export_ipc()), dtype=torch.uint8))
+    dist.broadcast(h, src=dst)
+    if rank == dst:
+        return ctx.frame_device_ptr()
+    return ctx.frame_open_ipc(bytes(h.cpu().numpy().tobytes()))
+
+
 def assemble_reference(gathered: torch.Tensor, height: int, tile_rows: int) -> torch.Tensor:
     """Pure-torch statement of vr_assemble_tiles (used on CPU tensors by the gloo tests and as
     the checker of the CUDA de-interleave kernel)."""
