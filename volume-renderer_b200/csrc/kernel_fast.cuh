@@ -611,6 +611,253 @@ march_texgather_kernel(const __grid_constant__ FrameConsts fc, const __grid_cons
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
 }
 
+// ------------------------------------------------------------------------------------------
+// z-pair texture-gather march ("texpair").  Third volume copy: a layered 2-D array of 32-bit
+// (16-bit for 8-bit data) texels, layer L in [0, Nz], texel (x, y, L) =
+//     v(x, y, max(L-1, 0))  |  v(x, y, min(L, Nz-1)) << bits
+// so that the layer iz+1 (iz = floor(fz) in [-1, Nz-1]) carries BOTH z slices of the trilinear
+// footprint with GL_CLAMP_TO_EDGE in z already applied.  ONE `tld4` per sample returns all
+// eight texels; x/y clamp-to-edge is the texture unit's address mode.  The texel offset
+// operand of tld4 (AOFFI, immediate {1,1}) moves the footprint from {i-1, i} to {i, i+1}, so
+// the gather coordinate is (float(ix), float(iy)) -- the corner shared by the four texels,
+// exact, half a texel from every footprint boundary -- and the `+1` add disappears.
+// Per sample vs march_ray_texgather: -1 tld4, -1 coordinate vector, -2 layer clamps, -1 add;
+// the TEX data pipe (76 % busy there) sees half the requests.  Costs 2x the source bytes in HBM.
+__device__ __forceinline__ void tld4_pair(cudaTextureObject_t tex, int layer, float x, float y,
+                                          uint32_t& t_x0y1, uint32_t& t_x1y1, uint32_t& t_x1y0, uint32_t& t_x0y0)
+{
+    asm volatile("tld4.r.a2d.v4.u32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}], {1, 1};"
+                 : "=r"(t_x0y1), "=r"(t_x1y1), "=r"(t_x1y0), "=r"(t_x0y0)
+                 : "l"(tex), "r"(layer), "f"(x), "f"(y));
+}
+
+// biased floats 2^23 + v of the two halves of a z-pair texel: one PRMT each
+template <typename T> __device__ __forceinline__ f2 unpack_zpair(uint32_t w);
+template <> __device__ __forceinline__ f2 unpack_zpair<uint16_t>(uint32_t w)
+{
+    return mk2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)));
+}
+template <> __device__ __forceinline__ f2 unpack_zpair<uint8_t>(uint32_t w)
+{
+    return mk2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)));
+}
+
+// C/A carry the ray's state in and out and `iter` counts samples already taken, so the loop also
+// finishes a ray whose partner in the two-ray kernel left the box first.
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTextureObject_t tex,
+                                                  const float pos0[3], const float dstep[3], float& outC, float& outA,
+                                                  int iter0 = 0)
+{
+    f2 pxy = mk2(pos0[0], pos0[1]);
+    float pz = pos0[2];
+    const f2 dxy = mk2(dstep[0], dstep[1]);
+    const float dz = dstep[2];
+    const f2 hxy = mk2(fc.half_len[0], fc.half_len[1]);
+    const float hz = fc.half_len[2];
+    const f2 ixy = mk2(fc.inv_denom[0], fc.inv_denom[1]);
+    const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
+    const float nz = fc.dimf[2];
+    const f2 mhalf = splat2(-0.5f), B2 = splat2(8388608.0f);
+    float C = outC, A = outA;
+    for (int iter = iter0; NOCAP || iter < 10000; ++iter) {
+        const f2 qxy = fadd(pxy, hxy);
+        const float qz = __fadd_rn(pz, hz);
+        f2 txy;
+        float tzq;
+        if (UNIT) { txy = qxy; tzq = qz; }
+        else if (TCDIV == DIV_RECIP_EXACT) { txy = fmul(qxy, ixy); tzq = __fmul_rn(qz, fc.inv_denom[2]); }
+        else {
+            const f2 q0 = fmul(qxy, ixy);
+            const f2 r = ffma(mk2(-fc.denom[0], -fc.denom[1]), q0, qxy);
+            txy = ffma(r, ixy, q0);
+            tzq = div_by<DIV_MARKSTEIN>(qz, fc.denom[2], fc.inv_denom[2]);
+        }
+        const float tz = __fsub_rn(1.0f, tzq);
+        const unsigned m = max(max(__float_as_uint(lo(txy)), __float_as_uint(hi(txy))), __float_as_uint(tz));
+        if (m > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) break;           // :118
+        const f2 fxy = ffma(txy, nxy, mhalf);
+        const float fz = __fmaf_rn(tz, nz, -0.5f);
+        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
+        const float flx = (float)ix, fly = (float)iy;
+        uint32_t t01, t11, t10, t00;                                   // suffix = x,y offsets; halves = (z, z+1)
+        tld4_pair(tex, iz + 1, flx, fly, t01, t11, t10, t00);
+        const float wx = __fsub_rn(lo(fxy), flx), wy = __fsub_rn(hi(fxy), fly);
+        const float wz = __fsub_rn(fz, (float)iz);
+        const f2 wxx = splat2(wx), wyy = splat2(wy);
+        const f2 loA = unpack_zpair<T>(t00), hiA = unpack_zpair<T>(t10);   // row y
+        const f2 loB = unpack_zpair<T>(t01), hiB = unpack_zpair<T>(t11);   // row y+1
+        const f2 cA = ffma(wxx, fsub(hiA, loA), fsub(loA, B2));
+        const f2 cB = ffma(wxx, fsub(hiB, loB), fsub(loB, B2));
+        const f2 cy = ffma(wyy, fsub(cB, cA), cA);
+        const float s = __fmaf_rn(wz, __fsub_rn(hi(cy), lo(cy)), lo(cy));
+        float v;
+        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
+        const float a = __fmul_rn(v, fc.alpha_scale);
+        const float c = __fmul_rn(v, a);
+        const float t = __fsub_rn(1.0f, A);
+        const f2 ca_t = fmul(mk2(c, a), splat2(t));
+        C = __fadd_rn(C, lo(ca_t));
+        A = __fadd_rn(A, hi(ca_t));
+        pxy = fadd(pxy, dxy);
+        pz = __fadd_rn(pz, dz);
+    }
+    outC = C; outA = A;
+}
+
+// Two rays (horizontally adjacent pixels) per thread over the same z-pair array: every IEEE
+// operation of the sample -- position, tex-coord, texel coordinate, weights, the seven lerps,
+// window, compositing products -- is issued ONCE as a packed f32x2 instruction for both rays
+// (lane .x = even pixel, .y = odd pixel); per thread and iteration 2 tld4 fetch 16 texels.  Sums
+// fed by an unfused product stay scalar (ptxas would contract them).  Returns the `done` bits;
+// the survivor of a pair is finished by march_ray_texpair.
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ unsigned march_rays2_texpair(const FrameConsts& fc, cudaTextureObject_t tex,
+                                                        f2 pos[3], const f2 ds[3], f2& C, f2& A, int& iter)
+{
+    const f2 hx = splat2(fc.half_len[0]), hy = splat2(fc.half_len[1]), hz = splat2(fc.half_len[2]);
+    const f2 nx = splat2(fc.dimf[0]), ny = splat2(fc.dimf[1]), nz = splat2(fc.dimf[2]);
+    const f2 mhalf = splat2(-0.5f), B2 = splat2(8388608.0f), one2 = splat2(1.0f);
+    const f2 alpha = splat2(fc.alpha_scale), vfmin = splat2(fc.fmin);
+    unsigned done = 0;
+    for (; NOCAP || iter < 10000; ++iter) {
+        const f2 qx = fadd(pos[0], hx), qy = fadd(pos[1], hy), qz = fadd(pos[2], hz);
+        f2 tx, ty, tz;
+        if (UNIT) { tx = qx; ty = qy; tz = fsub(one2, qz); }
+        else {
+            tx = div_by_l<TCDIV>(qx, fc.denom[0], fc.inv_denom[0]);
+            ty = div_by_l<TCDIV>(qy, fc.denom[1], fc.inv_denom[1]);
+            tz = fsub_after_mul(one2, div_by_l<TCDIV>(qz, fc.denom[2], fc.inv_denom[2]));
+        }
+        // :118 for both rays at once (bit patterns; no -0 / NaN on this path); which ray it was
+        // is worked out after the loop
+        const unsigned m0 = max(max(__float_as_uint(lo(tx)), __float_as_uint(lo(ty))), __float_as_uint(lo(tz)));
+        const unsigned m = max(max(m0, __float_as_uint(hi(tx))), max(__float_as_uint(hi(ty)), __float_as_uint(hi(tz))));
+        if (m > 0x3F800000u || max(__float_as_uint(lo(A)), __float_as_uint(hi(A))) >= 0x3F733333u) {
+            const unsigned m1 = max(max(__float_as_uint(hi(tx)), __float_as_uint(hi(ty))), __float_as_uint(hi(tz)));
+            if (m0 > 0x3F800000u || __float_as_uint(lo(A)) >= 0x3F733333u) done |= 1u;
+            if (m1 > 0x3F800000u || __float_as_uint(hi(A)) >= 0x3F733333u) done |= 2u;
+            break;
+        }
+        const f2 fx = ffma(tx, nx, mhalf), fy = ffma(ty, ny, mhalf), fz = ffma(tz, nz, mhalf);
+        const int ix0 = __float2int_rd(lo(fx)), iy0 = __float2int_rd(lo(fy)), iz0 = __float2int_rd(lo(fz));
+        const int ix1 = __float2int_rd(hi(fx)), iy1 = __float2int_rd(hi(fy)), iz1 = __float2int_rd(hi(fz));
+        const float flx0 = (float)ix0, fly0 = (float)iy0, flx1 = (float)ix1, fly1 = (float)iy1;
+        uint32_t a01, a11, a10, a00, b01, b11, b10, b00;               // ray 0 (a), ray 1 (b); suffix = x,y offsets
+        tld4_pair(tex, iz0 + 1, flx0, fly0, a01, a11, a10, a00);
+        tld4_pair(tex, iz1 + 1, flx1, fly1, b01, b11, b10, b00);
+        const f2 wx = fsub(fx, mk2(flx0, flx1)), wy = fsub(fy, mk2(fly0, fly1));
+        const f2 wz = fsub(fz, mk2((float)iz0, (float)iz1));
+        // biased floats 2^23 + v, paired across the two rays: L = slice z, H = slice z+1
+        const f2 za00 = unpack_zpair<T>(a00), za10 = unpack_zpair<T>(a10), za01 = unpack_zpair<T>(a01), za11 = unpack_zpair<T>(a11);
+        const f2 zb00 = unpack_zpair<T>(b00), zb10 = unpack_zpair<T>(b10), zb01 = unpack_zpair<T>(b01), zb11 = unpack_zpair<T>(b11);
+        const f2 L00 = mk2(lo(za00), lo(zb00)), H00 = mk2(hi(za00), hi(zb00));
+        const f2 L10 = mk2(lo(za10), lo(zb10)), H10 = mk2(hi(za10), hi(zb10));
+        const f2 L01 = mk2(lo(za01), lo(zb01)), H01 = mk2(hi(za01), hi(zb01));
+        const f2 L11 = mk2(lo(za11), lo(zb11)), H11 = mk2(hi(za11), hi(zb11));
+        const f2 c00 = ffma(wx, fsub(L10, L00), fsub(L00, B2));
+        const f2 c10 = ffma(wx, fsub(L11, L01), fsub(L01, B2));
+        const f2 c01 = ffma(wx, fsub(H10, H00), fsub(H00, B2));
+        const f2 c11 = ffma(wx, fsub(H11, H01), fsub(H01, B2));
+        const f2 c0 = ffma(wy, fsub(c10, c00), c00);
+        const f2 c1 = ffma(wy, fsub(c11, c01), c01);
+        const f2 s = ffma(wz, fsub(c1, c0), c0);
+        f2 v;                                                           // :122-124
+        if (WIN == WIN_COVERS0) v = div_by_l<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        else {
+            const f2 cl = mk2(fminf(fmaxf(lo(s), fc.fmin), fc.fmax), fminf(fmaxf(hi(s), fc.fmin), fc.fmax));
+            v = div_by_l<DIV_MARKSTEIN>(fsub(cl, vfmin), fc.frange, fc.inv_frange);
+        }
+        const f2 a = fmul(v, alpha);                                    // :130-132
+        const f2 c = fmul(v, a);
+        const f2 t = fsub(one2, A);
+        C = fadd_after_mul(C, fmul(c, t));
+        A = fadd_after_mul(A, fmul(a, t));
+        pos[0] = fadd(pos[0], ds[0]);                                   // :136
+        pos[1] = fadd(pos[1], ds[1]);
+        pos[2] = fadd(pos[2], ds[2]);
+    }
+    return done;
+}
+
+// CTA = 256 threads = 64 x 8 pixels; a warp covers 16 x 4 pixels (8 x 4 threads, 2 pixels each).
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+march_texpair2_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px0 = (blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7)) * 2;
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px0 >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const bool have1 = (px0 + 1) < fc.W;
+    const RaySetup r0 = setup_ray(fc, px0, py);
+    const RaySetup r1 = setup_ray(fc, have1 ? px0 + 1 : px0, py);
+    float p0[3], p1[3], d0[3], d1[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        p0[i] = __fadd_rn(__fadd_rn(r0.org[i], __fmul_rn(r0.dir[i], r0.t_min)), __fmul_rn(r0.dir[i], 0.000001f));
+        p1[i] = __fadd_rn(__fadd_rn(r1.org[i], __fmul_rn(r1.dir[i], r1.t_min)), __fmul_rn(r1.dir[i], 0.000001f));
+        d0[i] = __fmul_rn(r0.dir[i], fc.step);
+        d1[i] = __fmul_rn(r1.dir[i], fc.step);
+    }
+    float C0 = 0.f, A0 = 0.f, C1 = 0.f, A1 = 0.f;
+    unsigned alive = (r0.hit ? 1u : 0u) | ((r1.hit && have1) ? 2u : 0u);
+    int iter = 0;
+    if (alive == 3u) {
+        f2 pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pos[i] = mk2(p0[i], p1[i]); ds[i] = mk2(d0[i], d1[i]); }
+        f2 C = mk2(0.f, 0.f), A = mk2(0.f, 0.f);
+        const unsigned done = march_rays2_texpair<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A, iter);
+        C0 = lo(C); C1 = hi(C); A0 = lo(A); A1 = hi(A);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p0[i] = lo(pos[i]); p1[i] = hi(pos[i]); }
+        alive &= ~done;
+        if (!NOCAP && iter >= 10000) alive = 0;
+    }
+    if (alive) {   // finish whichever ray is still marching
+        const bool second = (alive & 2u) != 0;
+        float pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { pos[i] = second ? p1[i] : p0[i]; ds[i] = second ? d1[i] : d0[i]; }
+        float C = second ? C1 : C0, A = second ? A1 : A0;
+        march_ray_texpair<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A, iter);
+        if (second) { C1 = C; A1 = A; } else { C0 = C; A0 = A; }
+    }
+    const int orow = fc.compact ? lrow : py;
+    float4* out = reinterpret_cast<float4*>(args.out) + (size_t)orow * fc.W;
+    out[px0] = make_float4(C0, C0, C0, A0);
+    if (have1) out[px0 + 1] = make_float4(C1, C1, C1, A1);
+}
+
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__global__ void __launch_bounds__(256, NOCAP ? 8 : 6)
+march_texpair_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const RaySetup r = setup_ray(fc, px, py);
+    float C = 0.0f, A = 0.0f;
+    if (r.hit) {
+        float pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
+            ds[i] = __fmul_rn(r.dir[i], fc.step);
+        }
+        march_ray_texpair<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A);
+    }
+    const int orow = fc.compact ? lrow : py;
+    reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
+}
+
 // launch bounds measured on the headline frame: the capless loop fits 32 registers (8 CTAs/SM,
 // 3.50 ms); with the iteration counter 32 registers spill (4.31 ms) and 40 are best (3.78 ms)
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>

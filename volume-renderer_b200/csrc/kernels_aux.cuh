@@ -49,6 +49,22 @@ __global__ void pad_pairs_kernel(const T* __restrict__ src, W* __restrict__ dst,
     }
 }
 
+// ---- ingest: z-pair words for the texpair kernel ------------------------------------------------
+// Layers [l0, l0+nl) of the z-pair array: word (x, y, L) = v(x, y, max(L-1,0)) | v(x, y, min(L,nz-1)) << bits.
+// L runs over [0, nz]: the layer iz+1 of a sample with iz = floor(fz) in [-1, nz-1] holds both z slices
+// of its trilinear footprint, GL_CLAMP_TO_EDGE in z already applied (RendererCore.cpp:413).
+template <typename T, typename W>
+__global__ void zpair_pack_kernel(const T* __restrict__ src, W* __restrict__ dst, int nx, int ny, int nz, int l0, int nl)
+{
+    const uint64_t per_layer = (uint64_t)nx * ny, n = per_layer * (uint64_t)nl;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int L = l0 + (int)(i / per_layer);
+        const uint64_t xy = i % per_layer;
+        const int za = max(L - 1, 0), zb = min(L, nz - 1);
+        dst[i] = (W)((W)src[(uint64_t)za * per_layer + xy] | ((W)src[(uint64_t)zb * per_layer + xy] << (8 * sizeof(T))));
+    }
+}
+
 // ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
 template <typename T>
 __global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)

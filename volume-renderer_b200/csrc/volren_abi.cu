@@ -2,9 +2,11 @@
 //
 // Host code in this file evaluates the per-frame constants (frame.h) and must be compiled
 // with -Xcompiler -ffp-contract=off.  There is no CPU fallback anywhere in this library.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -67,6 +69,9 @@ struct vr_context {
     // second copy for the texture-gather kernel: layered 2-D array (layer = z), point sampling
     cudaArray_t d_arr = nullptr;
     cudaTextureObject_t tex = 0;
+    // third copy for the z-pair gather kernel: layered 2-D array of (z, z+1) words, Nz+1 layers
+    cudaArray_t d_arr2 = nullptr;
+    cudaTextureObject_t tex2 = 0;
     float voxel_size[3] = {1.f, 1.f, 1.f};
     vr_volume_stats stats{};
     bool have_stats = false;
@@ -258,6 +263,66 @@ int launch_texgather(vr_context* c, const LaunchPlan& plan, float* d_out, cudaSt
     return VR_OK;
 }
 
+template <typename T, int WIN>
+void launch_texpair_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+}
+
+int launch_texpair(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    vr::TexArgs a{};
+    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
+    bool unit, recip, nocap;
+    packed_flags(c, plan, &unit, &recip, &nocap);
+    if (c->bpv == 2) {
+        if (win == vr::WIN_COVERS0) launch_texpair_tw<uint16_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_tw<uint16_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+    } else {
+        if (win == vr::WIN_COVERS0) launch_texpair_tw<uint8_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_tw<uint8_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+    }
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+template <typename T, int WIN, int MINB>
+void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, true, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
+}
+
+// two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
+int launch_texpair2(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    vr::TexArgs a{};
+    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 grid((c->W + 63) / 64, (plan.local_rows + 7) / 8);
+    bool unit, recip, nocap;
+    packed_flags(c, plan, &unit, &recip, &nocap);
+    static const int minb = [] { const char* e = std::getenv("VR_TEXPAIR2_MINB"); return e ? std::atoi(e) : 5; }();
+#define VR_TP2(T, WIN) do { if (minb == 4) launch_texpair2_tw<T, WIN, 4>(plan.fc, a, grid, s, unit, recip, nocap); \
+                            else           launch_texpair2_tw<T, WIN, 5>(plan.fc, a, grid, s, unit, recip, nocap); } while (0)
+    if (c->bpv == 2) { if (win == vr::WIN_COVERS0) VR_TP2(uint16_t, vr::WIN_COVERS0); else VR_TP2(uint16_t, vr::WIN_CLAMP); }
+    else             { if (win == vr::WIN_COVERS0) VR_TP2(uint8_t, vr::WIN_COVERS0);  else VR_TP2(uint8_t, vr::WIN_CLAMP); }
+#undef VR_TP2
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
 template <typename T>
 int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
@@ -305,8 +370,11 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const int win = (c->params.min_val == 0 && c->have_stats && c->stats.max_value <= c->params.max_val)
                         ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
+    const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
-    if (want == VR_KERNEL_AUTO) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
+    if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
+    if (want == VR_KERNEL_TEXPAIR2 && !texpair_ok) want = VR_KERNEL_TEXPAIR;
+    if (want == VR_KERNEL_TEXPAIR && !texpair_ok) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
     if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
     if (want == VR_KERNEL_FAST && !fast_ok) want = VR_KERNEL_DIRECT;
@@ -319,6 +387,14 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
         // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
         cudaGetLastError();
         want = VR_KERNEL_FAST;
+    }
+    if (want == VR_KERNEL_TEXPAIR2) {
+        *used = VR_KERNEL_TEXPAIR2;
+        return launch_texpair2(c, plan, d_out, s, win);
+    }
+    if (want == VR_KERNEL_TEXPAIR) {
+        *used = VR_KERNEL_TEXPAIR;
+        return launch_texpair(c, plan, d_out, s, win);
     }
     if (want == VR_KERNEL_TEXGATHER) {
         *used = VR_KERNEL_TEXGATHER;
@@ -411,6 +487,42 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
             }
         }
         cudaGetLastError();     // without the array the LDG kernels serve every frame
+    }
+    // z-pair array for the texpair kernel: Nz+1 layers of (z, z+1) words, packed and copied in
+    // chunks of layers through a bounded staging buffer
+    if (c->tex2) { cudaDestroyTextureObject(c->tex2); c->tex2 = 0; }
+    if (c->d_arr2) { cudaFreeArray(c->d_arr2); c->d_arr2 = nullptr; }
+    if (nz + 1 <= 2048 && nx <= 32768 && ny <= 32768) {
+        typedef typename vr::PairWord<T>::type W;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(W), 0, 0, 0, cudaChannelFormatKindUnsigned);
+        cudaArray_t arr = nullptr;
+        W* d_stage = nullptr;
+        const uint64_t per_layer = (uint64_t)nx * ny;
+        const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nz + 1, (256ull << 20) / (per_layer * sizeof(W))));
+        bool ok = cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz + 1), cudaArrayLayered) == cudaSuccess &&
+                  cudaMalloc(&d_stage, per_layer * (uint64_t)chunk * sizeof(W)) == cudaSuccess;
+        for (int l0 = 0; ok && l0 <= nz; l0 += chunk) {
+            const int nl = std::min(chunk, nz + 1 - l0);
+            vr::zpair_pack_kernel<T, W><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, d_stage, nx, ny, nz, l0, nl);
+            cudaMemcpy3DParms cp = {};
+            cp.srcPtr = make_cudaPitchedPtr(d_stage, (size_t)nx * sizeof(W), nx, ny);
+            cp.dstArray = arr; cp.dstPos = make_cudaPos(0, 0, l0);
+            cp.extent = make_cudaExtent(nx, ny, nl); cp.kind = cudaMemcpyDeviceToDevice;
+            ok = cudaGetLastError() == cudaSuccess && cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess;
+        }
+        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (d_stage) cudaFree(d_stage);
+        cudaTextureObject_t tex = 0;
+        if (ok) {
+            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+            ok = cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess;
+        }
+        if (ok) { c->d_arr2 = arr; c->tex2 = tex; }
+        else if (arr) cudaFreeArray(arr);
+        cudaGetLastError();     // without the array the other kernels serve every frame
     }
     if (c->d_vol) cudaFree(c->d_vol);
     c->d_vol = d_new; c->vol_bytes = bytes;
@@ -510,6 +622,8 @@ void vr_destroy(vr_context* c)
     vr::windowed_release(c->win);
     if (c->tex) cudaDestroyTextureObject(c->tex);
     if (c->d_arr) cudaFreeArray(c->d_arr);
+    if (c->tex2) cudaDestroyTextureObject(c->tex2);
+    if (c->d_arr2) cudaFreeArray(c->d_arr2);
     if (c->d_vol) cudaFree(c->d_vol);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_rgb8) cudaFree(c->d_rgb8);
@@ -611,7 +725,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXGATHER)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXPAIR2)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         VR_CUDA(cudaSetDevice(c->device));
