@@ -706,6 +706,131 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTex
     outC = C; outA = A;
 }
 
+// Software-pipelined form of march_ray_texpair.  The loop above keeps ONE tld4 in flight per
+// warp; 64 warps x 16 writeback cycles per tld4 then cover only ~73 % of the texture unit's
+// return path while every warp waits a full queue length for its own fetch (ncu:
+// l1tex__tex_writeback_active 73 %, long_scoreboard).  The gather coordinates of sample i+1
+// depend only on `pos`, never on fetched data, so its tld4 is issued BEFORE sample i is
+// unpacked, interpolated and composited: two fetches in flight per warp.  Scheduling only --
+// the operation sequence per sample, and hence every bit of the result, is unchanged.  The
+// look-ahead fetch is skipped when sample i+1 lies outside the box.
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, cudaTextureObject_t tex,
+                                                       const float pos0[3], const float dstep[3], float& outC, float& outA,
+                                                       int iter0 = 0)
+{
+    f2 pxy = mk2(pos0[0], pos0[1]);
+    float pz = pos0[2];
+    const f2 dxy = mk2(dstep[0], dstep[1]);
+    const float dz = dstep[2];
+    const f2 hxy = mk2(fc.half_len[0], fc.half_len[1]);
+    const float hz = fc.half_len[2];
+    const f2 ixy = mk2(fc.inv_denom[0], fc.inv_denom[1]);
+    const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
+    const float nz = fc.dimf[2];
+    const f2 mhalf = splat2(-0.5f), B2 = splat2(8388608.0f);
+    float C = outC, A = outA;
+
+    // tex-coord of the sample at (pxy, pz): cartesianToTextureCoord :175-192; returns the :118 range key
+    auto tex_coord_key = [&](f2& txy, float& tz) -> unsigned {
+        const f2 qxy = fadd(pxy, hxy);
+        const float qz = __fadd_rn(pz, hz);
+        float tzq;
+        if (UNIT) { txy = qxy; tzq = qz; }
+        else if (TCDIV == DIV_RECIP_EXACT) { txy = fmul(qxy, ixy); tzq = __fmul_rn(qz, fc.inv_denom[2]); }
+        else {
+            const f2 q0 = fmul(qxy, ixy);
+            const f2 r = ffma(mk2(-fc.denom[0], -fc.denom[1]), q0, qxy);
+            txy = ffma(r, ixy, q0);
+            tzq = div_by<DIV_MARKSTEIN>(qz, fc.denom[2], fc.inv_denom[2]);
+        }
+        tz = __fsub_rn(1.0f, tzq);
+        return max(max(__float_as_uint(lo(txy)), __float_as_uint(hi(txy))), __float_as_uint(tz));
+    };
+
+    struct Fetched { uint32_t t01, t11, t10, t00; float wx, wy, wz; };
+    const unsigned last_layer = (unsigned)fc.dim[2];
+
+    // texel coordinates, weights and the gather of the sample whose tex-coord is (txy, tz).  The layer is
+    // clamped because a look-ahead sample may lie one step outside the box (its texels are never used).
+    auto fetch = [&](f2 txy, float tz, Fetched& f) {
+        const f2 fxy = ffma(txy, nxy, mhalf);
+        const float fz = __fmaf_rn(tz, nz, -0.5f);
+        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
+        const float flx = (float)ix, fly = (float)iy;
+        tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
+        f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
+    };
+    // interpolate, window, composite one fetched sample (:121-132)
+    auto consume = [&](const Fetched& f) {
+        const f2 wxx = splat2(f.wx), wyy = splat2(f.wy);
+        const f2 loA = unpack_zpair<T>(f.t00), hiA = unpack_zpair<T>(f.t10);   // row y
+        const f2 loB = unpack_zpair<T>(f.t01), hiB = unpack_zpair<T>(f.t11);   // row y+1
+        const f2 cA = ffma(wxx, fsub(hiA, loA), fsub(loA, B2));
+        const f2 cB = ffma(wxx, fsub(hiB, loB), fsub(loB, B2));
+        const f2 cy = ffma(wyy, fsub(cB, cA), cA);
+        const float s = __fmaf_rn(f.wz, __fsub_rn(hi(cy), lo(cy)), lo(cy));
+        float v;
+        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
+        const float a = __fmul_rn(v, fc.alpha_scale);
+        const float c = __fmul_rn(v, a);
+        const float t = __fsub_rn(1.0f, A);
+        const f2 ca_t = fmul(mk2(c, a), splat2(t));
+        C = __fadd_rn(C, lo(ca_t));
+        A = __fadd_rn(A, hi(ca_t));
+    };
+    // one pipeline stage: look ahead to sample i+1 (advance :136, range key :118, gather), then finish
+    // sample i.  Returns false when sample i+1 must not be taken.
+    auto stage = [&](const Fetched& cur, Fetched& nxt) -> bool {
+        pxy = fadd(pxy, dxy);
+        pz = __fadd_rn(pz, dz);
+        f2 txy; float tz;
+        const bool inside_n = tex_coord_key(txy, tz) <= 0x3F800000u;
+        fetch(txy, tz, nxt);
+        consume(cur);
+        return inside_n && __float_as_uint(A) < 0x3F733333u;
+    };
+
+    {
+        f2 txy; float tz;
+        if (tex_coord_key(txy, tz) > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return;   // :118, first sample
+        Fetched fa, fb;                                                // ping-pong: no register rotation
+        fetch(txy, tz, fa);
+        for (int iter = iter0; NOCAP || iter < 10000; iter += 2) {
+            if (!stage(fa, fb)) break;
+            if (!NOCAP && iter + 1 >= 10000) break;
+            if (!stage(fb, fa)) break;
+        }
+    }
+    outC = C; outA = A;
+}
+
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const RaySetup r = setup_ray(fc, px, py);
+    float C = 0.0f, A = 0.0f;
+    if (r.hit) {
+        float pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
+            ds[i] = __fmul_rn(r.dir[i], fc.step);
+        }
+        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A);
+    }
+    const int orow = fc.compact ? lrow : py;
+    reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
+}
+
 // Two rays (horizontally adjacent pixels) per thread over the same z-pair array: every IEEE
 // operation of the sample -- position, tex-coord, texel coordinate, weights, the seven lerps,
 // window, compositing products -- is issued ONCE as a packed f32x2 instruction for both rays

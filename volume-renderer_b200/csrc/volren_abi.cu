@@ -305,6 +305,36 @@ void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 gr
     else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
 }
 
+template <typename T, int WIN, int MINB>
+void launch_texpair_pipe_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
+}
+
+// software-pipelined texpair (two gathers in flight per warp).  VR_PIPE_MINB=5 (lab): 48 registers.
+int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    vr::TexArgs a{};
+    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
+    bool unit, recip, nocap;
+    packed_flags(c, plan, &unit, &recip, &nocap);
+    static const int minb = [] { const char* e = std::getenv("VR_PIPE_MINB"); return e ? std::atoi(e) : 6; }();
+#define VR_TPP(T, WIN) do { if (minb == 5) launch_texpair_pipe_tw<T, WIN, 5>(plan.fc, a, grid, s, unit, recip, nocap); \
+                            else           launch_texpair_pipe_tw<T, WIN, 6>(plan.fc, a, grid, s, unit, recip, nocap); } while (0)
+    if (c->bpv == 2) { if (win == vr::WIN_COVERS0) VR_TPP(uint16_t, vr::WIN_COVERS0); else VR_TPP(uint16_t, vr::WIN_CLAMP); }
+    else             { if (win == vr::WIN_COVERS0) VR_TPP(uint8_t, vr::WIN_COVERS0);  else VR_TPP(uint8_t, vr::WIN_CLAMP); }
+#undef VR_TPP
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
 // two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
 int launch_texpair2(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
@@ -372,8 +402,8 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
-    if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
-    if (want == VR_KERNEL_TEXPAIR2 && !texpair_ok) want = VR_KERNEL_TEXPAIR;
+    if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
+    if ((want == VR_KERNEL_TEXPAIR2 || want == VR_KERNEL_TEXPAIR_PIPE) && !texpair_ok) want = VR_KERNEL_TEXPAIR;
     if (want == VR_KERNEL_TEXPAIR && !texpair_ok) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
     if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
@@ -387,6 +417,10 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
         // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
         cudaGetLastError();
         want = VR_KERNEL_FAST;
+    }
+    if (want == VR_KERNEL_TEXPAIR_PIPE) {
+        *used = VR_KERNEL_TEXPAIR_PIPE;
+        return launch_texpair_pipe(c, plan, d_out, s, win);
     }
     if (want == VR_KERNEL_TEXPAIR2) {
         *used = VR_KERNEL_TEXPAIR2;
@@ -725,7 +759,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXPAIR2)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXPAIR_PIPE)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         VR_CUDA(cudaSetDevice(c->device));
