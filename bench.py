@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
     ap.add_argument("--handoff", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU: peer = kernels store straight into rank 0's frame over NVLink (CUDA IPC) + barrier; "
+                    help="multi-GPU: peer = kernels store straight into rank 0's frame over NVLink (CUDA IPC), frame barrier in peer memory; "
                          "nccl = compact tiles, one NCCL gather, de-interleave kernel")
     return ap.parse_args()
 
@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)],
+                                          "-lms", "10", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -96,6 +96,13 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+
+    def wait_for_samples(self, n=1, timeout_s=5.0):
+        """nvidia-smi needs a moment to start: block until it has delivered n samples."""
+        t0 = time.perf_counter()
+        while self.proc and len(self.rows) < n and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.005)
+        return len(self.rows)
 
     def stop(self):
         if self.proc:
@@ -260,12 +267,22 @@ def run_ours(args):
         if int(flag.item()) == 0:
             handoff = "nccl"
 
-    def step():
+    frame_no = [0]
+
+    def step(release=True):
         if world == 1:
             st = ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
         elif handoff == "peer":
+            # no collective call at all: completion and reuse of rank 0's frame are ordered by the
+            # barrier words behind its pixels (NVLink peer memory), two one-thread kernels per frame
+            frame_no[0] += 1
+            if rank != 0:
+                ctx.peer_frame_release(peer_ptr, frame_no[0] - 1, is_owner=False, stream=sptr)
             st = ctx.render_device(peer_ptr, compact=False, stream=sptr)
-            torch.distributed.barrier()     # the only per-frame collective: everyone's stores have landed
+            ctx.peer_frame_arrive(peer_ptr, frame_no[0], world, is_owner=(rank == 0), stream=sptr)
+            if rank == 0 and release:
+                ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)
+            launches[0] += 2
         else:
             st = ctx.render_device(local.data_ptr(), compact=True, stream=sptr)
             vdist.gather_tiles(local, gathered, dst=0)
@@ -293,7 +310,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_for_samples(1)
     barrier()
+    idle_samples = len(sampler.rows)        # taken before the GPU was under load: not reported
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
@@ -313,25 +332,42 @@ def run_ours(args):
         if world == 1:
             ctx.render_to_host_ptr(pinned.data_ptr())
         else:
-            step()
+            step(release=False)
             if rank == 0:
                 if handoff == "peer":
+                    torch.cuda.current_stream().synchronize()       # arrival wait done: the frame is complete
                     ctx.read_frame_into(pinned.data_ptr())
+                    ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)   # consumed: may be overwritten
                 else:
                     pinned.copy_(frame, non_blocking=True)
                     torch.cuda.synchronize()
-            if handoff == "peer":
-                torch.distributed.barrier()  # rank 0 has consumed the frame before anyone overwrites it
     barrier()
     e2e_s = time.perf_counter() - t0
+    # a short timed region (multi-GPU frames take < 1 ms) can end before nvidia-smi has sampled it
+    # a few times: keep the same load running, untimed, until there are at least 5 samples under load
+    need_more = torch.tensor([1 if (rank == 0 and len(sampler.rows) - idle_samples < 5) else 0], dtype=torch.int32, device=dev)
+    for _ in range(200):
+        if world > 1:
+            torch.distributed.broadcast(need_more, src=0)
+        if int(need_more.item()) == 0:
+            break
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        need_more[0] = 1 if (rank == 0 and len(sampler.rows) - idle_samples < 5) else 0
+    if rank == 0:
+        sampler.rows = sampler.rows[idle_samples:]
     clocks = sampler.stop() if rank == 0 else None
 
     # N-GPU frame == 1-GPU frame (every kernel is bit-exact and pixels are independent)
     same_as_single = None
     if world > 1:
-        step()
+        step(release=False)
         if rank == 0:
+            torch.cuda.synchronize()
             multi = torch.from_numpy(ctx.read_frame()).to(dev) if handoff == "peer" else frame.clone()
+            if handoff == "peer":
+                ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)
         barrier()
         if rank == 0:
             ctx.set_partition(0, 1, TILE_ROWS)
@@ -341,6 +377,11 @@ def run_ours(args):
             same_as_single = bool(torch.equal(multi.view(torch.int32), single.view(torch.int32)))
             ctx.set_partition(rank, world, TILE_ROWS)
         barrier()
+
+    if handoff == "peer" and rank == 0:
+        pst = ctx.peer_frame_status(peer_ptr)
+        if pst["timed_out"] or pst["arrivals"] != frame_no[0] * world:
+            raise SystemExit(f"bench.py: peer-memory frame barrier failed: {pst}, expected {frame_no[0] * world} arrivals")
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -399,7 +440,7 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, hand-off: "
-                                  + {"none": "n/a", "peer": "peer stores into rank 0's frame over NVLink + barrier", "nccl": "one NCCL gather + de-interleave"}[handoff],
+                                  + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory; frame barrier = flag words in the same peer memory (no collective call)", "nccl": "one NCCL gather + de-interleave"}[handoff],
                    "multi_gpu_frame_equals_single_gpu_frame": same_as_single,
                    "l2": f"inputs larger than L2 ({nvox * bpv / 2**30:.2f} GiB volume vs 126 MB L2); no flush needed" if nvox * bpv > 2**28
                          else "volume fits in L2 (correctness/plumbing config)",

@@ -166,6 +166,20 @@ VR_API int vr_frame_device_ptr(vr_context* ctx, float** d_frame);
 VR_API int vr_frame_export_ipc(vr_context* ctx, unsigned char handle[64]);
 VR_API int vr_frame_open_ipc(vr_context* ctx, const unsigned char handle[64], float** d_peer_frame);
 VR_API int vr_frame_close_ipc(vr_context* ctx, float* d_peer_frame);
+/* Frame barrier in the same peer memory (three words behind the owner's pixels), replacing the
+ * per-frame NCCL barrier with two one-thread kernels in stream order:
+ *   arrive:  every rank, after rendering frame `frame_no` (1, 2, 3 ...) into d_target_frame: a
+ *            system-scope fence + atomic on the owner's arrival counter; on the owner additionally a
+ *            bounded spin until all `world` ranks have arrived -> the frame is complete on the stream.
+ *   release: owner, after consuming frame `frame_no`: publishes it; other ranks, before rendering
+ *            frame_no + 1: bounded spin on the owner's word over NVLink.
+ * Spins give up after 5 s and set the timed_out word (vr_peer_frame_status); they never hang the GPU. */
+VR_API int vr_peer_frame_arrive(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int world,
+                                int is_owner, void* cuda_stream);
+VR_API int vr_peer_frame_release(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int is_owner,
+                                 void* cuda_stream);
+VR_API int vr_peer_frame_status(vr_context* ctx, float* d_target_frame, uint32_t* arrivals,
+                                uint32_t* released, uint32_t* timed_out);
 
 /* ---- display/save step after the path: float RGBA -> RGB8 (clamp, no gamma), vertical
  *      flip; replaces glBlitFramebuffer/glReadPixels, RendererCore.cpp:158-171 ---- */

@@ -65,3 +65,59 @@ def test_peer_stores_assemble_the_frame_in_rank0(tmp_path, world):
     out = str(tmp_path / "ok.npy")
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert np.load(out)[0] == 1
+
+
+def _worker_device_barrier(rank, world, port, out_path):
+    """Several frames back to back with NO host-side collective between them: completion and reuse of
+    rank 0's frame are ordered only by the barrier words in peer memory (vr_peer_frame_arrive/release)."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import volren_b200 as vb
+    import scenarios
+    dev = rank if torch.cuda.device_count() >= world else 0
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    W, H, tile_rows, frames = 200, 150, 16, 6
+    alphas = [0.05, 0.4, 0.11, 0.9, 0.02, 0.3]
+    ok = 1
+    with vb.Context(W, H, device=dev) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(cam)
+        refs = []
+        if rank == 0:
+            for a in alphas:
+                ctx.set_params(vb.default_params(alpha_scale=a, min_val=0, max_val=255, filter=1))
+                refs.append(ctx.render()[0])
+        handle = [ctx.frame_export_ipc() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        ptr = ctx.frame_device_ptr() if rank == 0 else ctx.frame_open_ipc(handle[0])
+        ctx.set_partition(rank, world, tile_rows)
+        dist.barrier()                                               # setup only; none inside the frame loop
+        for f in range(1, frames + 1):
+            ctx.set_params(vb.default_params(alpha_scale=alphas[f - 1], min_val=0, max_val=255, filter=1))
+            if rank != 0:
+                ctx.peer_frame_release(ptr, f - 1, is_owner=False)   # rank 0 is done with the previous frame
+            ctx.render_device(ptr, compact=False)
+            ctx.peer_frame_arrive(ptr, f, world, is_owner=(rank == 0))
+            if rank == 0:
+                got = ctx.read_frame()                               # same stream: after the arrival wait
+                if not np.array_equal(got.view(np.uint32), refs[f - 1].view(np.uint32)):
+                    ok = 0
+                ctx.peer_frame_release(ptr, f, is_owner=True)
+        if rank == 0:
+            st = ctx.peer_frame_status(ptr)
+            if st["timed_out"] or st["arrivals"] != frames * world or st["released"] != frames:
+                ok = 0
+            np.save(out_path, np.array([ok]))
+        dist.barrier()
+        if rank != 0:
+            ctx.frame_close_ipc(ptr)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_frame_barrier(tmp_path, world):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_device_barrier, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert np.load(out)[0] == 1

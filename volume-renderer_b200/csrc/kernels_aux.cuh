@@ -175,6 +175,45 @@ __global__ void rgba32f_to_rgb8_kernel(const float4* __restrict__ frame, uint8_t
     }
 }
 
+// ---- multi-GPU: frame barrier in NVLink peer memory ----------------------------------------------
+// Three words behind the owner's frame (same allocation, hence inside every peer's IPC mapping):
+// [0] arrivals (cumulative), [1] released frame number, [2] error (a wait gave up).
+// signal: every rank, in stream order after its march kernel -- the kernel boundary orders the
+// march's peer stores before the system-scope fence + atomic.  wait_*: bounded spins (globaltimer),
+// so a dead peer costs `timeout_ns`, never a hung GPU.
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void peer_signal_kernel(unsigned int* sync)
+{
+    __threadfence_system();
+    atomicAdd_system(&sync[0], 1u);
+}
+// word `idx` of `sync` >= target (wrap-safe), else error after timeout_ns
+__global__ void peer_wait_kernel(unsigned int* sync, int idx, unsigned int target, unsigned long long timeout_ns)
+{
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(&sync[idx]) - target) < 0) {
+        if (global_ns() - t0 > timeout_ns) { atomicExch_system(&sync[2], 1u); break; }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+__global__ void peer_release_kernel(unsigned int* sync, unsigned int frame_no)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(&sync[1]), "r"(frame_no) : "memory");
+}
+
 __global__ void popcount_kernel(const unsigned int* __restrict__ bits, uint64_t nwords, unsigned long long* out)
 {
     unsigned long long acc = 0;

@@ -49,6 +49,10 @@ int cuda_fail(cudaError_t e, const char* what)
 
 inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// the frame allocation carries the peer-barrier words behind the pixels (kernels_aux.cuh)
+constexpr size_t FRAME_SYNC_BYTES = 256;
+inline size_t frame_alloc_bytes(int w, int h) { return (size_t)w * h * 4 * sizeof(float) + FRAME_SYNC_BYTES; }
+
 }  // namespace
 
 struct vr_context {
@@ -640,7 +644,8 @@ int vr_create(int device, int width, int height, vr_context** out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_frame, (size_t)width * height * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_frame, frame_alloc_bytes(width, height));
+    if (e == cudaSuccess) e = cudaMemset(c->d_frame + (size_t)width * height * 4, 0, FRAME_SYNC_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, 256 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flag, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->d_lut, 0, 256 * sizeof(float));
@@ -676,7 +681,8 @@ int vr_resize(vr_context* c, int width, int height)
         return fail(VR_ERR_INVALID, "vr_resize: image size out of range");
     VR_CUDA(cudaSetDevice(c->device));
     float* d_new = nullptr;
-    VR_CUDA(cudaMalloc(&d_new, (size_t)width * height * 4 * sizeof(float)));
+    VR_CUDA(cudaMalloc(&d_new, frame_alloc_bytes(width, height)));
+    VR_CUDA(cudaMemset(d_new + (size_t)width * height * 4, 0, FRAME_SYNC_BYTES));
     cudaFree(c->d_frame);
     if (c->d_rgb8) { cudaFree(c->d_rgb8); c->d_rgb8 = nullptr; }
     c->d_frame = d_new; c->W = width; c->H = height;
@@ -880,6 +886,48 @@ int vr_frame_close_ipc(vr_context* c, float* d_peer_frame)
     if (!c || !d_peer_frame) return fail(VR_ERR_INVALID, "vr_frame_close_ipc: null argument");
     VR_CUDA(cudaSetDevice(c->device));
     VR_CUDA(cudaIpcCloseMemHandle(d_peer_frame));
+    return VR_OK;
+}
+
+// the barrier words live behind the pixels of the frame `d_target_frame` points to (same W x H on every rank)
+static unsigned int* frame_sync_words(const vr_context* c, float* d_target_frame)
+{
+    return reinterpret_cast<unsigned int*>(d_target_frame + (size_t)c->W * c->H * 4);
+}
+
+int vr_peer_frame_arrive(vr_context* c, float* d_target_frame, uint32_t frame_no, int world, int is_owner, void* cuda_stream)
+{
+    if (!c || !d_target_frame || world < 1) return fail(VR_ERR_INVALID, "vr_peer_frame_arrive: bad argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    unsigned int* sync = frame_sync_words(c, d_target_frame);
+    vr::peer_signal_kernel<<<1, 1, 0, s>>>(sync);
+    if (is_owner) vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, 5000000000ull);
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+int vr_peer_frame_release(vr_context* c, float* d_target_frame, uint32_t frame_no, int is_owner, void* cuda_stream)
+{
+    if (!c || !d_target_frame) return fail(VR_ERR_INVALID, "vr_peer_frame_release: bad argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    unsigned int* sync = frame_sync_words(c, d_target_frame);
+    if (is_owner) vr::peer_release_kernel<<<1, 1, 0, s>>>(sync, frame_no);
+    else          vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 1, frame_no, 5000000000ull);
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+int vr_peer_frame_status(vr_context* c, float* d_target_frame, uint32_t* arrivals, uint32_t* released, uint32_t* timed_out)
+{
+    if (!c || !d_target_frame) return fail(VR_ERR_INVALID, "vr_peer_frame_status: bad argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    unsigned int w[3] = {0, 0, 0};
+    VR_CUDA(cudaMemcpy(w, frame_sync_words(c, d_target_frame), sizeof w, cudaMemcpyDeviceToHost));
+    if (arrivals) *arrivals = w[0];
+    if (released) *released = w[1];
+    if (timed_out) *timed_out = w[2];
     return VR_OK;
 }
 

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
     "vr_render", "vr_read_frame", "vr_render_device", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
     "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
+    "vr_peer_frame_arrive", "vr_peer_frame_release", "vr_peer_frame_status",
     "vr_upload_synthetic", "vr_synthetic_to_host",
 ]
 
@@ -112,6 +113,9 @@ def lib():
         L.vr_frame_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
         L.vr_frame_open_ipc.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.vr_frame_close_ipc.argtypes = [C.c_void_p, C.c_void_p]
+        L.vr_peer_frame_arrive.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+        L.vr_peer_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.vr_peer_frame_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.vr_count_frame.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.vr_upload_synthetic.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3), C.c_int, C.POINTER(C.c_float * 3),
                                           C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
@@ -278,6 +282,20 @@ class Context:
 
     def frame_close_ipc(self, ptr: int):
         _check(lib().vr_frame_close_ipc(self._h, C.c_void_p(ptr)))
+
+    # -- frame barrier in the same peer memory (replaces the per-frame NCCL barrier)
+    def peer_frame_arrive(self, target_ptr: int, frame_no: int, world: int, is_owner: bool, stream: int = 0):
+        _check(lib().vr_peer_frame_arrive(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, world, 1 if is_owner else 0,
+                                          C.c_void_p(stream)))
+
+    def peer_frame_release(self, target_ptr: int, frame_no: int, is_owner: bool, stream: int = 0):
+        _check(lib().vr_peer_frame_release(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, 1 if is_owner else 0,
+                                           C.c_void_p(stream)))
+
+    def peer_frame_status(self, target_ptr: int):
+        a, r, t = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().vr_peer_frame_status(self._h, C.c_void_p(target_ptr), C.byref(a), C.byref(r), C.byref(t)))
+        return {"arrivals": a.value, "released": r.value, "timed_out": t.value}
 
     def read_rgb8(self, flip_vertical: bool = True) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)
