@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--camera", default="K2", choices=["K0", "K1", "K2"])
     ap.add_argument("--alpha", type=float, default=0.02)
     ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu"])
     ap.add_argument("--cpu-row-stride", type=int, default=1, help="cpu_baseline renders every n-th row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
@@ -220,7 +220,7 @@ def run_ours(args):
     dims, bpv = cfg["dims"], cfg["bpv"]
     cam = workloads.camera_block(args.camera)
     kernel = {"auto": vb.KERNEL_AUTO, "direct": vb.KERNEL_DIRECT, "windowed": vb.KERNEL_WINDOWED, "fast": vb.KERNEL_FAST, "texgather": vb.KERNEL_TEXGATHER,
-              "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE}[args.kernel]
+              "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "hybrid": vb.KERNEL_HYBRID, "zlsu": vb.KERNEL_ZLSU}[args.kernel]
     params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
                                filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
                                step_scale=cfg["step_scale"], kernel=kernel)
@@ -403,7 +403,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel", 3: "march_packed_kernel" if args.filter == "trilinear" else "march_fast_kernel", 4: "march_texgather_kernel",
-                                                    5: "march_texpair_kernel", 6: "march_texpair2_kernel", 7: "march_texpair_pipe_kernel"}.get(used[0], "?"),
+                                                    5: "march_texpair_kernel", 6: "march_texpair2_kernel", 7: "march_texpair_pipe_kernel", 8: "march_texpair_pipe_kernel", 9: "march_texpair_pipe_kernel"}.get(used[0], "?"),
             "kernel_ms_avg": avg_kernel_ms}
     if counted is not None:
         owned_px = sum(min(TILE_ROWS, H - t0_ * TILE_ROWS) for t0_ in range(rank, (H + TILE_ROWS - 1) // TILE_ROWS, world)) * W

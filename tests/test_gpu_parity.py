@@ -27,8 +27,8 @@ def run_product(vox, dims, voxel_size, cam, W, H, vkw, kernel=vb.KERNEL_AUTO, pa
 
 @pytest.mark.parametrize("cid", [c[0] for c in scenarios.CASES])
 @pytest.mark.parametrize("kernel", [vb.KERNEL_DIRECT, vb.KERNEL_AUTO, vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER,
-                                    vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE],
-                         ids=["direct", "auto", "fast", "windowed", "texgather", "texpair", "texpair2", "texpair_pipe"])
+                                    vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU],
+                         ids=["direct", "auto", "fast", "windowed", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu"])
 def test_case_matches_oracle(cid, kernel):
     _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
     vox, dims, bpv, vs = scenarios.volume(vname)
@@ -70,12 +70,12 @@ def test_optimised_kernels_really_run_and_match(vname, cname, kw):
     cam = scenarios.camera(cname)
     W, H = 320, 200
     ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
-    for kernel in (vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_AUTO):
+    for kernel in (vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU, vb.KERNEL_AUTO):
         img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
         if kernel != vb.KERNEL_AUTO:
             assert st.kernel_used == kernel, f"requested kernel {kernel}, ran {st.kernel_used}"
         else:
-            assert st.kernel_used in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE)
+            assert st.kernel_used in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID)
         compare(img, ref, f"{vname}/{cname}/kernel{kernel}")
 
 
@@ -228,7 +228,7 @@ def test_full_size_1024_cube_sampled_rows():
         ctx.set_camera(cam)
         ctx.set_params(vb.default_params(**kw))
         img, st = ctx.render()
-        for kernel in (vb.KERNEL_DIRECT, vb.KERNEL_WINDOWED, vb.KERNEL_FAST, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE):      # every kernel, same bits, at full size
+        for kernel in (vb.KERNEL_DIRECT, vb.KERNEL_WINDOWED, vb.KERNEL_FAST, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU):      # every kernel, same bits, at full size
             ctx.set_params(vb.default_params(kernel=kernel, **kw))
             other, st2 = ctx.render()
             assert st2.kernel_used == kernel
@@ -257,7 +257,7 @@ def test_texpair_odd_image_sizes(W, H):
     cam = scenarios.camera("K1")
     kw = dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1)
     ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
-    for kernel in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE):
+    for kernel in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU):
         img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
         assert st.kernel_used == kernel
         compare(img, ref, f"texpair {W}x{H} kernel{kernel}")

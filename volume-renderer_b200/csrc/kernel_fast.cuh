@@ -582,6 +582,10 @@ struct TexArgs {
     cudaTextureObject_t tex;
     float* out;
     int local_rows;
+    // linear, edge-replicated copy of the z-pair words for the LSU stage of the hybrid kernel:
+    // (Nx+2) x (Ny+2) x (Nz+1) words, row pitch `zpitch`, slice stride `zslice` (words, < 2^31 in total)
+    const void* zlin;
+    int zpitch, zslice;
 };
 
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, bool FLOATTEX = false>
@@ -714,11 +718,22 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTex
 // unpacked, interpolated and composited: two fetches in flight per warp.  Scheduling only --
 // the operation sequence per sample, and hence every bit of the result, is unchanged.  The
 // look-ahead fetch is skipped when sample i+1 lies outside the box.
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP>
-__device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, cudaTextureObject_t tex,
+//
+// FA / FB select the fetch path of the two ping-pong stages (even / odd samples): FETCH_TEX is the tld4
+// above; FETCH_LSU reads the same four z-pair words with 4 ld.global.nc from a linear edge-replicated
+// copy.  The texture unit returns 32 B/clk/SM (measured: 16 writeback cycles per 32-bit tld4 warp
+// instruction) and is ~75 % busy when it serves every sample; alternating the two paths halves its
+// load and gives the otherwise idle LSU/L1 data pipe the other half.
+enum { FETCH_TEX = 0, FETCH_LSU = 1 };
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX>
+__device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, const TexArgs& args,
                                                        const float pos0[3], const float dstep[3], float& outC, float& outA,
                                                        int iter0 = 0)
 {
+    const cudaTextureObject_t tex = args.tex;
+    typedef typename PairWord<T>::type ZW;
+    const int zpitch = args.zpitch, zslice = args.zslice;
+    const ZW* __restrict__ zbase = static_cast<const ZW*>(args.zlin) + ((size_t)zslice + zpitch + 1);   // (ix, iy, iz) = (-1, -1, -1) lands on word 0
     f2 pxy = mk2(pos0[0], pos0[1]);
     float pz = pos0[2];
     const f2 dxy = mk2(dstep[0], dstep[1]);
@@ -753,12 +768,20 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, cu
 
     // texel coordinates, weights and the gather of the sample whose tex-coord is (txy, tz).  The layer is
     // clamped because a look-ahead sample may lie one step outside the box (its texels are never used).
-    auto fetch = [&](f2 txy, float tz, Fetched& f) {
+    auto fetch = [&](int path, f2 txy, float tz, bool inside, Fetched& f) {
         const f2 fxy = ffma(txy, nxy, mhalf);
         const float fz = __fmaf_rn(tz, nz, -0.5f);
         const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
         const float flx = (float)ix, fly = (float)iy;
-        tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
+        if (path == FETCH_TEX) {
+            tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
+        } else {
+            // an outside look-ahead sample reads word 0 instead (its texels are never used)
+            const int e = inside ? iz * zslice + (iy * zpitch + ix) : -(zslice + zpitch + 1);
+            const ZW* __restrict__ p0 = zbase + e;
+            const ZW* __restrict__ p1 = zbase + (e + zpitch);
+            f.t00 = __ldg(p0); f.t10 = __ldg(p0 + 1); f.t01 = __ldg(p1); f.t11 = __ldg(p1 + 1);
+        }
         f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
     };
     // interpolate, window, composite one fetched sample (:121-132)
@@ -782,12 +805,12 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, cu
     };
     // one pipeline stage: look ahead to sample i+1 (advance :136, range key :118, gather), then finish
     // sample i.  Returns false when sample i+1 must not be taken.
-    auto stage = [&](const Fetched& cur, Fetched& nxt) -> bool {
+    auto stage = [&](int path_n, const Fetched& cur, Fetched& nxt) -> bool {
         pxy = fadd(pxy, dxy);
         pz = __fadd_rn(pz, dz);
         f2 txy; float tz;
         const bool inside_n = tex_coord_key(txy, tz) <= 0x3F800000u;
-        fetch(txy, tz, nxt);
+        fetch(path_n, txy, tz, inside_n, nxt);
         consume(cur);
         return inside_n && __float_as_uint(A) < 0x3F733333u;
     };
@@ -796,17 +819,17 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, cu
         f2 txy; float tz;
         if (tex_coord_key(txy, tz) > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return;   // :118, first sample
         Fetched fa, fb;                                                // ping-pong: no register rotation
-        fetch(txy, tz, fa);
+        fetch(FA, txy, tz, true, fa);
         for (int iter = iter0; NOCAP || iter < 10000; iter += 2) {
-            if (!stage(fa, fb)) break;
+            if (!stage(FB, fa, fb)) break;
             if (!NOCAP && iter + 1 >= 10000) break;
-            if (!stage(fb, fa)) break;
+            if (!stage(FA, fb, fa)) break;
         }
     }
     outC = C; outA = A;
 }
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB>
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB, int FA = FETCH_TEX, int FB = FETCH_TEX>
 __global__ void __launch_bounds__(256, MINB)
 march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
 {
@@ -825,7 +848,7 @@ march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_c
             pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
             ds[i] = __fmul_rn(r.dir[i], fc.step);
         }
-        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A);
+        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP, FA, FB>(fc, args, pos, ds, C, A);
     }
     const int orow = fc.compact ? lrow : py;
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);

@@ -65,6 +65,15 @@ __global__ void zpair_pack_kernel(const T* __restrict__ src, W* __restrict__ dst
     }
 }
 
+// Linear copy of the same z-pair words for the LSU stage of the hybrid lab kernels, derived from the
+// padded volume (same pitch): word i = padded[i] | padded[i + slice] << bits, i over (nz+1) slices.
+template <typename T, typename W>
+__global__ void zpair_from_padded_kernel(const T* __restrict__ padded, W* __restrict__ dst, uint64_t slice, uint64_t nwords)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = (W)((W)padded[i] | ((W)padded[i + slice] << (8 * sizeof(T))));
+}
+
 // ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
 template <typename T>
 __global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)

@@ -76,6 +76,10 @@ struct vr_context {
     // third copy for the z-pair gather kernel: layered 2-D array of (z, z+1) words, Nz+1 layers
     cudaArray_t d_arr2 = nullptr;
     cudaTextureObject_t tex2 = 0;
+    // ... and the same words as a linear edge-replicated array for the LSU stage of the hybrid kernel
+    void* d_zlin = nullptr;
+    uint32_t zpitch = 0;                 // words
+    uint64_t zslice = 0;                 // words
     float voxel_size[3] = {1.f, 1.f, 1.f};
     vr_volume_stats stats{};
     bool have_stats = false;
@@ -309,34 +313,45 @@ void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 gr
     else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
 }
 
-template <typename T, int WIN, int MINB>
+template <typename T, int WIN, int FA, int FB>
 void launch_texpair_pipe_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
 {
     using namespace vr;
     const dim3 block(256);
-    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
+    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
 }
 
-// software-pipelined texpair (two gathers in flight per warp).  VR_PIPE_MINB=5 (lab): 48 registers.
-int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+template <int FA, int FB>
+int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
     vr::TexArgs a{};
     a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
+    a.zlin = c->d_zlin; a.zpitch = (int)c->zpitch; a.zslice = (int)c->zslice;
     const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
     bool unit, recip, nocap;
     packed_flags(c, plan, &unit, &recip, &nocap);
-    static const int minb = [] { const char* e = std::getenv("VR_PIPE_MINB"); return e ? std::atoi(e) : 6; }();
-#define VR_TPP(T, WIN) do { if (minb == 5) launch_texpair_pipe_tw<T, WIN, 5>(plan.fc, a, grid, s, unit, recip, nocap); \
-                            else           launch_texpair_pipe_tw<T, WIN, 6>(plan.fc, a, grid, s, unit, recip, nocap); } while (0)
-    if (c->bpv == 2) { if (win == vr::WIN_COVERS0) VR_TPP(uint16_t, vr::WIN_COVERS0); else VR_TPP(uint16_t, vr::WIN_CLAMP); }
-    else             { if (win == vr::WIN_COVERS0) VR_TPP(uint8_t, vr::WIN_COVERS0);  else VR_TPP(uint8_t, vr::WIN_CLAMP); }
-#undef VR_TPP
+    if (c->bpv == 2) {
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+    } else {
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+    }
     VR_CUDA(cudaGetLastError());
     return VR_OK;
+}
+
+// software-pipelined z-pair march (two fetches in flight per warp): texture gathers only, texture gather /
+// LSU alternating (hybrid), or LSU only
+int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win, int kernel)
+{
+    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU>(c, plan, d_out, s, win);
+    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU>(c, plan, d_out, s, win);
+    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX>(c, plan, d_out, s, win);
 }
 
 // two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
@@ -389,6 +404,29 @@ int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStrea
     return VR_OK;
 }
 
+// Linear copy of the z-pair words for the HYBRID / ZLSU lab kernels, built from the padded volume on
+// first use: word (jx, jy, L) = padded(jx, jy, L) | padded(jx, jy, L+1) << bits, same row pitch.
+template <typename T>
+bool ensure_zlin_t(vr_context* c)
+{
+    typedef typename vr::PairWord<T>::type W;
+    const uint64_t zslice = c->slice, zwords = zslice * (uint64_t)(c->dim[2] + 1);
+    if (zwords + zslice >= (1ull << 31)) return false;              // 32-bit word indices in the kernel
+    void* d_z = nullptr;
+    if (cudaMalloc(&d_z, zwords * sizeof(W) + 256) != cudaSuccess) { cudaGetLastError(); return false; }
+    vr::zpair_from_padded_kernel<T, W><<<c->sm_count * 16, 256, 0, c->stream>>>((const T*)c->d_vol, (W*)d_z, zslice, zwords);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(d_z); cudaGetLastError(); return false; }
+    c->d_zlin = d_z; c->zpitch = c->pitch; c->zslice = zslice;
+    return true;
+}
+
+bool ensure_zlin(vr_context* c)
+{
+    if (c->d_zlin) return true;
+    if (!c->d_vol || !c->tex2) return false;
+    return c->bpv == 1 ? ensure_zlin_t<uint8_t>(c) : ensure_zlin_t<uint16_t>(c);
+}
+
 // the march: returns which kernel ran
 int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, uint32_t* used,
                  uint32_t* launches)
@@ -407,6 +445,8 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
     if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
+    const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
+    if ((want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) && !zlin_ok) want = VR_KERNEL_TEXPAIR_PIPE;
     if ((want == VR_KERNEL_TEXPAIR2 || want == VR_KERNEL_TEXPAIR_PIPE) && !texpair_ok) want = VR_KERNEL_TEXPAIR;
     if (want == VR_KERNEL_TEXPAIR && !texpair_ok) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
@@ -422,9 +462,9 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
         cudaGetLastError();
         want = VR_KERNEL_FAST;
     }
-    if (want == VR_KERNEL_TEXPAIR_PIPE) {
-        *used = VR_KERNEL_TEXPAIR_PIPE;
-        return launch_texpair_pipe(c, plan, d_out, s, win);
+    if (want == VR_KERNEL_TEXPAIR_PIPE || want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) {
+        *used = (uint32_t)want;
+        return launch_texpair_pipe(c, plan, d_out, s, win, want);
     }
     if (want == VR_KERNEL_TEXPAIR2) {
         *used = VR_KERNEL_TEXPAIR2;
@@ -562,6 +602,7 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
         else if (arr) cudaFreeArray(arr);
         cudaGetLastError();     // without the array the other kernels serve every frame
     }
+    if (c->d_zlin) { cudaFree(c->d_zlin); c->d_zlin = nullptr; }      // rebuilt on demand (ensure_zlin)
     if (c->d_vol) cudaFree(c->d_vol);
     c->d_vol = d_new; c->vol_bytes = bytes;
     c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
@@ -663,6 +704,7 @@ void vr_destroy(vr_context* c)
     if (c->d_arr) cudaFreeArray(c->d_arr);
     if (c->tex2) cudaDestroyTextureObject(c->tex2);
     if (c->d_arr2) cudaFreeArray(c->d_arr2);
+    if (c->d_zlin) cudaFree(c->d_zlin);
     if (c->d_vol) cudaFree(c->d_vol);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_rgb8) cudaFree(c->d_rgb8);
@@ -765,7 +807,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_TEXPAIR_PIPE)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_ZLSU)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         VR_CUDA(cudaSetDevice(c->device));
