@@ -131,10 +131,11 @@ def test_row_tile_partition_equals_single_gpu(world, tile_rows):
 def test_volume_stats_match_reference_loops():
     """min/max + histogram kernels vs a numpy restatement of RendererCore.cpp:360-405."""
     rng = np.random.default_rng(3)
-    for bpv, hi in ((1, 256), (2, 3000)):
-        vox = rng.integers(0 if bpv == 1 else 17, hi, 50 * 40 * 30).astype(np.uint8 if bpv == 1 else np.uint16)
+    # (51, 41, 31): odd voxel count -> the scalar tail behind the 16-byte vector body; 65535: full u16 range
+    for bpv, hi, dims in ((1, 256, (50, 40, 30)), (2, 3000, (50, 40, 30)), (1, 256, (51, 41, 31)), (2, 65536, (51, 41, 31))):
+        vox = rng.integers(0 if bpv == 1 else 17, hi, dims[0] * dims[1] * dims[2]).astype(np.uint8 if bpv == 1 else np.uint16)
         with vb.Context(32, 32) as ctx:
-            ctx.upload_volume(vox, (50, 40, 30))
+            ctx.upload_volume(vox, dims)
             mn, mx, hist = ctx.volume_stats()
         if bpv == 1:
             assert (mn, mx) == (0, 255)
@@ -261,3 +262,25 @@ def test_texpair_odd_image_sizes(W, H):
         img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
         assert st.kernel_used == kernel
         compare(img, ref, f"texpair {W}x{H} kernel{kernel}")
+
+
+@pytest.mark.parametrize("vname,cname,kw", [
+    ("mix64_u8", "K1", dict(alpha_scale=0.3, min_val=0, max_val=255, filter=1, tf=True)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.08, min_val=30, max_val=200, filter=1, tf=True, step_scale=0.5)),
+    ("mix_64x64x32_u16", "K1", dict(alpha_scale=0.2, min_val=100, max_val=3900, filter=1, tf=True)),
+    ("rand_40x56x33_u16", "K2", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1, tf=True)),
+])
+def test_transfer_function_runs_on_the_pipelined_gather_kernel(vname, cname, kw):
+    """CubicSpline transfer function (BASELINE config 3): the opacity LUT is read inside the optimised
+    kernel -- no fallback to the generic DIRECT loop -- and the frame equals the oracle's bit for bit."""
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    cam = scenarios.camera(cname)
+    W, H = 320, 200
+    okw, vkw = scenarios.split_kwargs(kw)
+    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
+    img, st = run_product(vox, dims, vs, cam, W, H, vkw)
+    assert st.kernel_used == vb.KERNEL_TEXPAIR_PIPE
+    compare(img, ref, f"tf {vname}/{cname}")
+    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
+    assert st2.kernel_used == vb.KERNEL_DIRECT
+    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))

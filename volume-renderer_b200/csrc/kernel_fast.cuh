@@ -586,6 +586,7 @@ struct TexArgs {
     // (Nx+2) x (Ny+2) x (Nz+1) words, row pitch `zpitch`, slice stride `zslice` (words, < 2^31 in total)
     const void* zlin;
     int zpitch, zslice;
+    const float* tf_lut;        // 256-entry opacity LUT (transfer-function form of the pipelined kernel)
 };
 
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, bool FLOATTEX = false>
@@ -724,8 +725,20 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTex
 // copy.  The texture unit returns 32 B/clk/SM (measured: 16 writeback cycles per 32-bit tld4 warp
 // instruction) and is ~75 % busy when it serves every sample; alternating the two paths halves its
 // load and gives the otherwise idle LSU/L1 data pipe the other half.
+// lab only (upper bound for run-time specialisation): headline-frame constants as immediates
+#if defined(VR_LAB_IMM) && VR_LAB_IMM >= 1
+#define VR_KG(rt, imm) (imm)
+#else
+#define VR_KG(rt, imm) (rt)
+#endif
+#if defined(VR_LAB_IMM) && VR_LAB_IMM >= 2
+#define VR_KW(rt, imm) (imm)
+#else
+#define VR_KW(rt, imm) (rt)
+#endif
 enum { FETCH_TEX = 0, FETCH_LSU = 1 };
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX>
+// TF: transfer-function extension: src.a = lut[floor(v*255 + 0.5)], rgb stays v.
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX, bool TF = false>
 __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, const TexArgs& args,
                                                        const float pos0[3], const float dstep[3], float& outC, float& outA,
                                                        int iter0 = 0)
@@ -738,11 +751,11 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
     float pz = pos0[2];
     const f2 dxy = mk2(dstep[0], dstep[1]);
     const float dz = dstep[2];
-    const f2 hxy = mk2(fc.half_len[0], fc.half_len[1]);
-    const float hz = fc.half_len[2];
+    const f2 hxy = mk2(VR_KG(fc.half_len[0], 0.5f), VR_KG(fc.half_len[1], 0.5f));
+    const float hz = VR_KG(fc.half_len[2], 0.5f);
     const f2 ixy = mk2(fc.inv_denom[0], fc.inv_denom[1]);
-    const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
-    const float nz = fc.dimf[2];
+    const f2 nxy = mk2(VR_KG(fc.dimf[0], 1024.0f), VR_KG(fc.dimf[1], 1024.0f));
+    const float nz = VR_KG(fc.dimf[2], 1024.0f);
     const f2 mhalf = splat2(-0.5f), B2 = splat2(8388608.0f);
     float C = outC, A = outA;
 
@@ -764,7 +777,7 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
     };
 
     struct Fetched { uint32_t t01, t11, t10, t00; float wx, wy, wz; };
-    const unsigned last_layer = (unsigned)fc.dim[2];
+    const unsigned last_layer = VR_KG((unsigned)fc.dim[2], 1024u);
 
     // texel coordinates, weights and the gather of the sample whose tex-coord is (txy, tz).  The layer is
     // clamped because a look-ahead sample may lie one step outside the box (its texels are never used).
@@ -794,9 +807,15 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
         const f2 cy = ffma(wyy, fsub(cB, cA), cA);
         const float s = __fmaf_rn(f.wz, __fsub_rn(hi(cy), lo(cy)), lo(cy));
         float v;
-        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, VR_KW(fc.frange, 4095.0f), VR_KW(fc.inv_frange, 1.0f / 4095.0f));
         else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
-        const float a = __fmul_rn(v, fc.alpha_scale);
+        float src_a = v;
+        if (TF) {
+            // v in [0,1] on this path (ordered window), so the index is in [0,255]; the unsigned min only guards the load
+            const unsigned iso = min((unsigned)__float2int_rd(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f)), 255u);
+            src_a = __ldg(args.tf_lut + iso);
+        }
+        const float a = __fmul_rn(src_a, VR_KW(fc.alpha_scale, 0.02f));
         const float c = __fmul_rn(v, a);
         const float t = __fsub_rn(1.0f, A);
         const f2 ca_t = fmul(mk2(c, a), splat2(t));
@@ -829,7 +848,7 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
     outC = C; outA = A;
 }
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB, int FA = FETCH_TEX, int FB = FETCH_TEX>
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB, int FA = FETCH_TEX, int FB = FETCH_TEX, bool TF = false>
 __global__ void __launch_bounds__(256, MINB)
 march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
 {
@@ -848,7 +867,7 @@ march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_c
             pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
             ds[i] = __fmul_rn(r.dir[i], fc.step);
         }
-        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP, FA, FB>(fc, args, pos, ds, C, A);
+        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP, FA, FB, TF>(fc, args, pos, ds, C, A);
     }
     const int orow = fc.compact ? lrow : py;
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);

@@ -75,40 +75,115 @@ __global__ void zpair_from_padded_kernel(const T* __restrict__ padded, W* __rest
 }
 
 // ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
+// HBM-bound read of the whole volume: 16-byte loads (8 u16 / 16 u8 per thread and request), four
+// requests in flight per thread, scalar head/tail for unaligned ends.
+template <typename T>
+__device__ __forceinline__ void minmax_word(uint32_t w, unsigned int& lo, unsigned int& hi)
+{
+    if (sizeof(T) == 2) {
+        const unsigned int a = w & 0xffffu, b = w >> 16;
+        lo = min(lo, min(a, b)); hi = max(hi, max(a, b));
+    } else {
+        const unsigned int a = w & 0xffu, b = (w >> 8) & 0xffu, c = (w >> 16) & 0xffu, d = w >> 24;
+        lo = min(min(lo, min(a, b)), min(c, d)); hi = max(max(hi, max(a, b)), max(c, d));
+    }
+}
+
 template <typename T>
 __global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)
 {
     unsigned int lo = 0xffffffffu, hi = 0u;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned int v = src[i];
-        lo = min(lo, v); hi = max(hi, v);
+    constexpr uint64_t PER = 16 / sizeof(T);
+    const uint64_t head = min(n, (uint64_t)(((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / sizeof(T)));
+    const uint64_t nvec = (n - head) / PER;
+    const uint4* __restrict__ v = reinterpret_cast<const uint4*>(src + head);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = tid;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = __ldg(v + i), b = __ldg(v + i + stride), c = __ldg(v + i + 2 * stride), d = __ldg(v + i + 3 * stride);
+        minmax_word<T>(a.x, lo, hi); minmax_word<T>(a.y, lo, hi); minmax_word<T>(a.z, lo, hi); minmax_word<T>(a.w, lo, hi);
+        minmax_word<T>(b.x, lo, hi); minmax_word<T>(b.y, lo, hi); minmax_word<T>(b.z, lo, hi); minmax_word<T>(b.w, lo, hi);
+        minmax_word<T>(c.x, lo, hi); minmax_word<T>(c.y, lo, hi); minmax_word<T>(c.z, lo, hi); minmax_word<T>(c.w, lo, hi);
+        minmax_word<T>(d.x, lo, hi); minmax_word<T>(d.y, lo, hi); minmax_word<T>(d.z, lo, hi); minmax_word<T>(d.w, lo, hi);
     }
+    for (; i < nvec; i += stride) {
+        const uint4 a = __ldg(v + i);
+        minmax_word<T>(a.x, lo, hi); minmax_word<T>(a.y, lo, hi); minmax_word<T>(a.z, lo, hi); minmax_word<T>(a.w, lo, hi);
+    }
+    // scalar head and tail
+    for (uint64_t k = tid; k < head; k += stride) { const unsigned int x = src[k]; lo = min(lo, x); hi = max(hi, x); }
+    for (uint64_t k = head + nvec * PER + tid; k < n; k += stride) { const unsigned int x = src[k]; lo = min(lo, x); hi = max(hi, x); }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
     if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
 }
 
 // ---- ingest: 256-bin histogram (RendererCore.cpp:386-398) ---------------------------------
-// 8-bit: bin = value; 16-bit: bin = round(value * 255.0f / max_dataset_val); bin 0 skipped.
-template <typename T>
-__global__ void histogram_kernel(const T* __restrict__ src, uint64_t n, float max_dataset_val,
-                                 unsigned long long* out_bins)
+// 8-bit: bin = value; 16-bit: bin = round(value * 255.0f / max_dataset_val) as the reference computes
+// it (float multiply, IEEE divide, round half away, assignment to uint16_t :394); bin 0 and bins > 255
+// are skipped.  The 16-bit mapping depends on the value only, so it is tabulated once per upload
+// (65536 entries, 0 = skip) and the scan itself is an HBM-bound read: 16-byte loads, the table in
+// shared memory, one 256-bin counter set per warp, runs of equal bins merged before the atomic.
+__global__ void histogram_lut_kernel(float max_dataset_val, uint8_t* __restrict__ lut)
 {
-    __shared__ unsigned int bins[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned int v = src[i];
-        if (sizeof(T) == 2) {
-            const float scaled = roundf(fdiv(fmul((float)v, 255.0f), max_dataset_val));
-            v = (unsigned int)scaled & 0xffffu;      // assignment to uint16_t, RendererCore.cpp:394
-        }
-        if (v == 0 || v > 255) continue;
-        atomicAdd(&bins[v], 1u);
+    const unsigned int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= 65536u) return;
+    const float scaled = roundf(fdiv(fmul((float)v, 255.0f), max_dataset_val));
+    const unsigned int b = (unsigned int)scaled & 0xffffu;      // assignment to uint16_t, RendererCore.cpp:394
+    lut[v] = (b == 0 || b > 255) ? 0 : (uint8_t)b;
+}
+
+constexpr int HIST_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(HIST_THREADS)
+histogram_kernel(const T* __restrict__ src, uint64_t n, const uint8_t* __restrict__ lut, unsigned long long* out_bins)
+{
+    extern __shared__ __align__(16) unsigned char hist_smem[];
+    unsigned int* wbins = reinterpret_cast<unsigned int*>(hist_smem);                  // [warps][256]
+    uint8_t* slut = hist_smem + (HIST_THREADS / 32) * 256 * sizeof(unsigned int);        // [65536], 16-bit data only
+    for (int i = threadIdx.x; i < (HIST_THREADS / 32) * 256; i += blockDim.x) wbins[i] = 0;
+    if (sizeof(T) == 2) {
+        const uint4* g = reinterpret_cast<const uint4*>(lut);
+        uint4* d = reinterpret_cast<uint4*>(slut);
+        for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) d[i] = __ldg(g + i);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-        if (bins[i]) atomicAdd(&out_bins[i], (unsigned long long)bins[i]);
+    unsigned int* mine = wbins + (threadIdx.x >> 5) * 256;
+    unsigned int cur = 0, cnt = 0;
+    auto add = [&](unsigned int b) {
+        if (b == cur) { ++cnt; return; }
+        if (cur) atomicAdd(&mine[cur], cnt);
+        cur = b; cnt = 1;
+    };
+    auto add_word = [&](uint32_t w) {
+        if (sizeof(T) == 2) { add(slut[w & 0xffffu]); add(slut[w >> 16]); }
+        else { add(w & 0xffu); add((w >> 8) & 0xffu); add((w >> 16) & 0xffu); add(w >> 24); }
+    };
+    constexpr uint64_t PER = 16 / sizeof(T);
+    const uint64_t head = min(n, (uint64_t)(((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / sizeof(T)));
+    const uint64_t nvec = (n - head) / PER;
+    const uint4* __restrict__ v = reinterpret_cast<const uint4*>(src + head);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = tid;
+    for (; i + stride < nvec; i += 2 * stride) {
+        const uint4 a = __ldg(v + i), b = __ldg(v + i + stride);
+        add_word(a.x); add_word(a.y); add_word(a.z); add_word(a.w);
+        add_word(b.x); add_word(b.y); add_word(b.z); add_word(b.w);
+    }
+    for (; i < nvec; i += stride) {
+        const uint4 a = __ldg(v + i);
+        add_word(a.x); add_word(a.y); add_word(a.z); add_word(a.w);
+    }
+    for (uint64_t k = tid; k < head; k += stride) add(sizeof(T) == 2 ? (unsigned int)slut[src[k]] : (unsigned int)src[k]);
+    for (uint64_t k = head + nvec * PER + tid; k < n; k += stride) add(sizeof(T) == 2 ? (unsigned int)slut[src[k]] : (unsigned int)src[k]);
+    if (cur) atomicAdd(&mine[cur], cnt);
+    __syncthreads();
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        unsigned int t = 0;
+        for (int w = 0; w < HIST_THREADS / 32; ++w) t += wbins[w * 256 + b];
+        if (t) atomicAdd(&out_bins[b], (unsigned long long)t);
+    }
 }
 
 // ---- synthetic volume `mix` --------------------------------------------------

@@ -88,6 +88,7 @@ struct vr_context {
     bool have_cam = false;
     vr_params params;
     float* d_lut = nullptr;
+    bool lut_fast_ok = false;            // every LUT entry finite and >= +0
     int rank = 0, world = 1, tile_rows = 8;
     // Markstein verification cache: divisor bits -> ok
     std::map<uint32_t, bool> div_ok;
@@ -165,7 +166,10 @@ int make_plan(vr_context* c, int compact, LaunchPlan* plan)
     plan->local_rows = compact_rows_of(c->H, c->rank, c->world, c->tile_rows);
 
     const vr_params& p = c->params;
-    bool generic = p.is_mip == 1 || p.use_tf != 0 || p.view_top == 1 || p.view_bottom == 1 ||
+    // the transfer-function LUT alone does not need the generic loop: the pipelined gather kernel has a TF form
+    const bool tf_fast = p.use_tf != 0 && c->lut_fast_ok && c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
+                         (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
+    bool generic = p.is_mip == 1 || (p.use_tf != 0 && !tf_fast) || p.view_top == 1 || p.view_bottom == 1 ||
                    fc.opacity_correction || !(p.max_val > p.min_val);
     if (!generic) {
         bool ok = false;
@@ -319,33 +323,34 @@ void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 gr
     else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
 }
 
-template <typename T, int WIN, int FA, int FB>
+template <typename T, int WIN, int FA, int FB, bool TF>
 void launch_texpair_pipe_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
 {
     using namespace vr;
     const dim3 block(256);
-    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB><<<grid, block, 0, s>>>(fc, a);
+    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
 }
 
-template <int FA, int FB>
+template <int FA, int FB, bool TF>
 int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
     vr::TexArgs a{};
     a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
     a.zlin = c->d_zlin; a.zpitch = (int)c->zpitch; a.zslice = (int)c->zslice;
+    a.tf_lut = c->d_lut;
     const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
     bool unit, recip, nocap;
     packed_flags(c, plan, &unit, &recip, &nocap);
     if (c->bpv == 2) {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
     } else {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB>(plan.fc, a, grid, s, unit, recip, nocap);
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
     }
     VR_CUDA(cudaGetLastError());
     return VR_OK;
@@ -355,9 +360,10 @@ int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, c
 // LSU alternating (hybrid), or LSU only
 int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win, int kernel)
 {
-    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU>(c, plan, d_out, s, win);
-    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU>(c, plan, d_out, s, win);
-    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX>(c, plan, d_out, s, win);
+    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU, false>(c, plan, d_out, s, win);
+    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU, false>(c, plan, d_out, s, win);
+    if (plan.fc.use_tf)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, true>(c, plan, d_out, s, win);
+    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, false>(c, plan, d_out, s, win);
 }
 
 // two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
@@ -450,6 +456,7 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
+    if (fc.use_tf && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
     if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
     if ((want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) && !zlin_ok) want = VR_KERNEL_TEXPAIR_PIPE;
@@ -530,8 +537,21 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
         VR_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
         VR_CUDA(cudaStreamSynchronize(c->stream));
     }
-    vr::histogram_kernel<T><<<blocks, 256, 0, c->stream>>>(d_src, n, (float)(int)mm[1], d_bins);
-    VR_CUDA(cudaGetLastError());
+    {
+        uint8_t* d_hlut = nullptr;
+        size_t smem = (vr::HIST_THREADS / 32) * 256 * sizeof(unsigned int);
+        if (sizeof(T) == 2) {
+            VR_CUDA(cudaMalloc(&d_hlut, 65536));
+            vr::histogram_lut_kernel<<<65536 / 256, 256, 0, c->stream>>>((float)(int)mm[1], d_hlut);
+            smem += 65536;
+            VR_CUDA(cudaFuncSetAttribute(vr::histogram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        vr::histogram_kernel<T><<<c->sm_count * 3, vr::HIST_THREADS, smem, c->stream>>>(d_src, n, d_hlut, d_bins);
+        cudaError_t he = cudaGetLastError();
+        if (he == cudaSuccess) he = cudaStreamSynchronize(c->stream);
+        if (d_hlut) cudaFree(d_hlut);
+        if (he != cudaSuccess) { cudaFree(d_mm); cudaFree(d_bins); return cuda_fail(he, "histogram_kernel"); }
+    }
     unsigned long long bins[256];
     VR_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof bins, cudaMemcpyDeviceToHost, c->stream));
 
@@ -821,6 +841,10 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_ZLSU)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
+        // the optimised loop tests ranges on float bit patterns: it needs a finite, non-negative opacity LUT
+        bool ok = true;
+        for (int i = 0; i < 256; ++i) ok = ok && std::isfinite(p->tf_lut[i]) && p->tf_lut[i] >= 0.0f && !std::signbit(p->tf_lut[i]);
+        c->lut_fast_ok = ok;
         VR_CUDA(cudaSetDevice(c->device));
         VR_CUDA(cudaMemcpyAsync(c->d_lut, p->tf_lut, 256 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         VR_CUDA(cudaStreamSynchronize(c->stream));

@@ -15,7 +15,7 @@ import numpy as np
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # volume-renderer_b200/
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libvolren_b200.so")
+LIB_PATH = os.environ.get("VOLREN_B200_LIB") or os.path.join(LIB_DIR, "libvolren_b200.so")   # env override: lab builds
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libvolren_host.so")
 
 FILTER_NEAREST, FILTER_TRILINEAR = 0, 1
