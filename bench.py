@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu"])
     ap.add_argument("--cpu-row-stride", type=int, default=1, help="cpu_baseline renders every n-th row")
+    ap.add_argument("--mip", action="store_true", help="maximum-intensity projection (the reference's use_mip toggle)")
     ap.add_argument("--tf", action="store_true", help="CubicSpline transfer function (default alpha knots of the reference's TF editor)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
@@ -70,7 +71,7 @@ def workload(args):
     cfg["window"] = (0, cfg["vmax"])
     cfg["name"] = (f"{args.config}: {cfg['dims'][0]}x{cfg['dims'][1]}x{cfg['dims'][2]} uint{8 * cfg['bpv']} synthetic mix, "
                    f"{cfg['image'][0]}x{cfg['image'][1]}, step_scale {cfg['step_scale']}, camera {args.camera}, "
-                   f"alpha {args.alpha}, {args.filter}" + (", CubicSpline TF" if args.tf else ""))
+                   f"alpha {args.alpha}, {args.filter}" + (", CubicSpline TF" if args.tf else "") + (", MIP" if args.mip else ""))
     return cfg
 
 
@@ -161,7 +162,7 @@ def cpu_march(cfg, args, host_vol, cam, row_stride, nthreads):
     p = orc.make_params(W, H, cfg["dims"], cfg["bpv"], cam, alpha_scale=args.alpha,
                         min_val=cfg["window"][0], max_val=cfg["window"][1],
                         filter=1 if args.filter == "trilinear" else 0, step_scale=cfg["step_scale"],
-                        tf_lut=default_tf_lut() if args.tf else None,
+                        tf_lut=default_tf_lut() if args.tf else None, is_mip=1 if args.mip else 0,
                         row_begin=row_stride // 2, row_stride=row_stride)
     t0 = time.perf_counter()
     img, cnt, _ = orc.render(p, host_vol, nthreads=nthreads)
@@ -231,7 +232,8 @@ def run_ours(args):
               "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "hybrid": vb.KERNEL_HYBRID, "zlsu": vb.KERNEL_ZLSU}[args.kernel]
     params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
                                filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
-                               step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None)
+                               step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None,
+                               is_mip=1 if args.mip else 0)
 
     ctx = vb.Context(W, H, device=local_rank)
     want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)

@@ -737,8 +737,11 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTex
 #define VR_KW(rt, imm) (rt)
 #endif
 enum { FETCH_TEX = 0, FETCH_LSU = 1 };
-// TF: transfer-function extension: src.a = lut[floor(v*255 + 0.5)], rgb stays v.
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX, bool TF = false>
+// MODE: MODE_DVR = rayMarchVolume (:104-139); MODE_TF = the same with the transfer-function extension
+// (SURVEY 8a-7): src.a = lut[floor(v*255 + 0.5)], rgb stays v; MODE_MIP = MIP (:141-173): dest = max over
+// the samples of v*alpha_scale, with the inherited `dest.a >= 0.95` exit of :156.
+enum { MODE_DVR = 0, MODE_TF = 1, MODE_MIP = 2 };
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX, int MODE = MODE_DVR>
 __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, const TexArgs& args,
                                                        const float pos0[3], const float dstep[3], float& outC, float& outA,
                                                        int iter0 = 0)
@@ -809,8 +812,13 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
         float v;
         if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, VR_KW(fc.frange, 4095.0f), VR_KW(fc.inv_frange, 1.0f / 4095.0f));
         else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
+        if (MODE == MODE_MIP) {
+            const float m = __fmul_rn(v, VR_KW(fc.alpha_scale, 0.02f));            // :163
+            if (A < m) { C = m; A = m; }                                           // :164-167
+            return;
+        }
         float src_a = v;
-        if (TF) {
+        if (MODE == MODE_TF) {
             // v in [0,1] on this path (ordered window), so the index is in [0,255]; the unsigned min only guards the load
             const unsigned iso = min((unsigned)__float2int_rd(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f)), 255u);
             src_a = __ldg(args.tf_lut + iso);
@@ -848,7 +856,7 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
     outC = C; outA = A;
 }
 
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB, int FA = FETCH_TEX, int FB = FETCH_TEX, bool TF = false>
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int MINB, int FA = FETCH_TEX, int FB = FETCH_TEX, int MODE = MODE_DVR>
 __global__ void __launch_bounds__(256, MINB)
 march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
 {
@@ -867,7 +875,7 @@ march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_c
             pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
             ds[i] = __fmul_rn(r.dir[i], fc.step);
         }
-        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP, FA, FB, TF>(fc, args, pos, ds, C, A);
+        march_ray_texpair_pipe<T, TCDIV, WIN, UNIT, NOCAP, FA, FB, MODE>(fc, args, pos, ds, C, A);
     }
     const int orow = fc.compact ? lrow : py;
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);

@@ -169,7 +169,10 @@ int make_plan(vr_context* c, int compact, LaunchPlan* plan)
     // the transfer-function LUT alone does not need the generic loop: the pipelined gather kernel has a TF form
     const bool tf_fast = p.use_tf != 0 && c->lut_fast_ok && c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
                          (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
-    bool generic = p.is_mip == 1 || (p.use_tf != 0 && !tf_fast) || p.view_top == 1 || p.view_bottom == 1 ||
+    const bool pipe_selectable = c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
+                                 (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
+    const bool mip_fast = p.is_mip == 1 && p.use_tf == 0 && pipe_selectable;      // ... and a MIP form
+    bool generic = (p.is_mip == 1 && !mip_fast) || (p.use_tf != 0 && !(tf_fast && p.is_mip != 1)) || p.view_top == 1 || p.view_bottom == 1 ||
                    fc.opacity_correction || !(p.max_val > p.min_val);
     if (!generic) {
         bool ok = false;
@@ -323,19 +326,19 @@ void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 gr
     else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
 }
 
-template <typename T, int WIN, int FA, int FB, bool TF>
+template <typename T, int WIN, int FA, int FB, int MODE>
 void launch_texpair_pipe_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
 {
     using namespace vr;
     const dim3 block(256);
-    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB, TF><<<grid, block, 0, s>>>(fc, a);
+    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
+    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
 }
 
-template <int FA, int FB, bool TF>
+template <int FA, int FB, int MODE>
 int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
 {
     vr::TexArgs a{};
@@ -346,11 +349,11 @@ int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, c
     bool unit, recip, nocap;
     packed_flags(c, plan, &unit, &recip, &nocap);
     if (c->bpv == 2) {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
     } else {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB, TF>(plan.fc, a, grid, s, unit, recip, nocap);
+        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
+        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
     }
     VR_CUDA(cudaGetLastError());
     return VR_OK;
@@ -360,10 +363,11 @@ int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, c
 // LSU alternating (hybrid), or LSU only
 int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win, int kernel)
 {
-    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU, false>(c, plan, d_out, s, win);
-    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU, false>(c, plan, d_out, s, win);
-    if (plan.fc.use_tf)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, true>(c, plan, d_out, s, win);
-    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, false>(c, plan, d_out, s, win);
+    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
+    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
+    if (plan.fc.is_mip)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_MIP>(c, plan, d_out, s, win);
+    if (plan.fc.use_tf)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_TF>(c, plan, d_out, s, win);
+    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR>(c, plan, d_out, s, win);
 }
 
 // two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
@@ -456,7 +460,7 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
-    if (fc.use_tf && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
+    if ((fc.use_tf || fc.is_mip) && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
     if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
     if ((want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) && !zlin_ok) want = VR_KERNEL_TEXPAIR_PIPE;
