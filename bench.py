@@ -333,14 +333,45 @@ def run_ours(args):
     timed_launches = launches[0]
     timed_kernel_ms = list(kernel_ms)
 
-    # e2e: through the C-ABI with host buffers, copies inside the timed region
+    # e2e: through the C-ABI with host buffers, copies inside the timed region.
+    # N > 1: one host frame in shared memory, page-locked in every rank process; each rank copies its own
+    # row tiles device->host over its own PCIe link (vr_render_owned_to_host) -- N links instead of rank 0's one.
+    shared = None
+    if world > 1:
+        ok = 1
+        name = f"volren_b200_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        for creating in (True, False):                            # rank 0 creates, barrier, the others attach
+            try:
+                if creating == (rank == 0):
+                    shared = vdist.SharedHostFrame(name, W, H, rank, world, create=creating)
+            except Exception as e:
+                ok = 0
+                print(f"bench.py: rank {rank}: shared host frame unavailable ({e}); rank 0 reads the frame back alone", file=sys.stderr)
+            if creating:
+                torch.distributed.barrier()
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if shared is not None:
+                shared.close()
+            shared = None
+    e2e_mode = "single GPU: vr_render (row bands overlap the device->host copy)" if world == 1 else \
+               ("every rank copies its own row tiles into one shared page-locked host frame" if shared is not None
+                else "hand-off to rank 0 on the device, rank 0 copies the frame to the host")
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         ctx.set_camera(cam)
         ctx.set_params(params)
         if world == 1:
             ctx.render_to_host_ptr(pinned.data_ptr())
+        elif shared is not None:
+            shared.wait_released(i)                                   # the consumer is done with the previous frame
+            ctx.render_owned_to_host_ptr(shared.frame_ptr)
+            shared.mark_done(i + 1)
+            if rank == 0:
+                shared.wait_all_done(i + 1)                           # the whole frame is in host memory
+                shared.release(i + 1)
         else:
             step(release=False)
             if rank == 0:
@@ -371,6 +402,7 @@ def run_ours(args):
 
     # N-GPU frame == 1-GPU frame (every kernel is bit-exact and pixels are independent)
     same_as_single = None
+    host_same = None
     if world > 1:
         step(release=False)
         if rank == 0:
@@ -385,6 +417,8 @@ def run_ours(args):
             ctx.render_device(single.data_ptr(), compact=False, stream=sptr)
             torch.cuda.synchronize()
             same_as_single = bool(torch.equal(multi.view(torch.int32), single.view(torch.int32)))
+            if shared is not None:
+                host_same = bool(np.array_equal(shared.frame.view(np.uint32), single.cpu().numpy().view(np.uint32)))
             ctx.set_partition(rank, world, TILE_ROWS)
         barrier()
 
@@ -398,6 +432,10 @@ def run_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    if shared is not None:
+        if world > 1:
+            torch.distributed.barrier()
+        shared.close()
     if peer_ptr and rank != 0:
         ctx.frame_close_ipc(peer_ptr)
     if rank != 0:
@@ -452,6 +490,7 @@ def run_ours(args):
         "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, hand-off: "
                                   + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory; frame barrier = flag words in the same peer memory (no collective call)", "nccl": "one NCCL gather + de-interleave"}[handoff],
                    "multi_gpu_frame_equals_single_gpu_frame": same_as_single,
+                   "e2e_path": e2e_mode, "multi_gpu_host_frame_equals_single_gpu_frame": host_same,
                    "l2": f"inputs larger than L2 ({nvox * bpv / 2**30:.2f} GiB volume vs 126 MB L2); no flush needed" if nvox * bpv > 2**28
                          else "volume fits in L2 (correctness/plumbing config)",
                    "kernel": roof["kernel"]},

@@ -155,6 +155,11 @@ VR_API int vr_render(vr_context* ctx, float* host_rgba, vr_render_stats* stats);
 VR_API int vr_read_frame(vr_context* ctx, float* host_rgba);
 VR_API int vr_render_device(vr_context* ctx, float* d_rgba, int compact, void* cuda_stream,
                             vr_render_stats* stats);
+/* multi-GPU end to end (no reference counterpart): render this rank's row tiles (vr_set_partition) and copy
+ * them into their rows of a FULL W x H host frame; with one host buffer shared by all rank processes
+ * (shared memory, page-locked in each) every GPU's own PCIe link carries its share of the frame.  Rows
+ * owned by other ranks are left untouched.  Synchronous. */
+VR_API int vr_render_owned_to_host(vr_context* ctx, float* host_full_frame, vr_render_stats* stats);
 /* rank-major compact tiles [world][owned rows][W][4] -> full frame, on the device
  * (the de-interleave after the NCCL gather) */
 VR_API int vr_assemble_tiles(vr_context* ctx, const float* d_gathered, float* d_frame,

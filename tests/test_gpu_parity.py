@@ -305,3 +305,28 @@ def test_mip_runs_on_the_pipelined_gather_kernel(vname, cname, kw):
     direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
     assert st2.kernel_used == vb.KERNEL_DIRECT
     assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
+
+
+@pytest.mark.parametrize("world,tile_rows", [(2, 16), (3, 4), (8, 16)])
+def test_owned_tiles_to_host_frame_assemble_the_frame(world, tile_rows):
+    """Multi-GPU end to end (vr_render_owned_to_host): every rank copies only its own row tiles into a
+    full host frame; all ranks together (emulated on one device) reproduce the unpartitioned frame."""
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    W, H = 200, 150
+    kw = dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)
+    full, _ = run_product(vox, dims, vs, cam, W, H, kw)
+    host = np.full((H, W, 4), np.nan, dtype=np.float32)
+    with vb.Context(W, H) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(cam)
+        ctx.set_params(vb.default_params(**kw))
+        for rank in range(world):
+            ctx.set_partition(rank, world, tile_rows)
+            before = host.copy()
+            st = ctx.render_owned_to_host_ptr(host.ctypes.data)
+            assert st.kernel_launches >= 1
+            owned = ((np.arange(H) // tile_rows) % world) == rank
+            # rows of other ranks are untouched
+            assert np.array_equal(host[~owned].view(np.uint32), before[~owned].view(np.uint32))
+    assert np.array_equal(host.view(np.uint32), full.view(np.uint32))

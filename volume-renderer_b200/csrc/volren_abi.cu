@@ -969,6 +969,30 @@ int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
     return VR_OK;
 }
 
+// Multi-GPU end to end: this rank's row tiles straight into a FULL host frame (one buffer shared by all
+// ranks, e.g. POSIX shared memory registered with cudaHostRegister in every process): N PCIe links carry
+// the frame instead of rank 0's one, and nothing crosses NVLink.  Rows this rank does not own are not touched.
+int vr_render_owned_to_host(vr_context* c, float* host_full_frame, vr_render_stats* stats)
+{
+    if (!c || !host_full_frame) return fail(VR_ERR_INVALID, "vr_render_owned_to_host: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = render_common(c, c->d_frame, /*compact=*/1, c->stream, stats);     // compact tiles fit in the frame buffer
+    if (rc != VR_OK) return rc;
+    const int tiles = (c->H + c->tile_rows - 1) / c->tile_rows;
+    const size_t row_floats = (size_t)c->W * 4;
+    int local_tile = 0;
+    for (int t = c->rank; t < tiles; t += c->world, ++local_tile) {
+        const int y0 = t * c->tile_rows, rows = std::min(c->tile_rows, c->H - y0);
+        VR_CUDA(cudaMemcpyAsync(host_full_frame + (size_t)y0 * row_floats,
+                                c->d_frame + (size_t)local_tile * c->tile_rows * row_floats,
+                                (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
 int vr_read_frame(vr_context* c, float* host_rgba)
 {
     if (!c || !host_rgba) return fail(VR_ERR_INVALID, "vr_read_frame: null argument");

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "vr_create", "vr_destroy", "vr_resize", "vr_image_size",
     "vr_upload_volume", "vr_upload_volume_device", "vr_set_voxel_size", "vr_volume_stats_get",
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
-    "vr_render", "vr_read_frame", "vr_render_device", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
+    "vr_render", "vr_read_frame", "vr_render_device", "vr_render_owned_to_host", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
     "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
     "vr_peer_frame_arrive", "vr_peer_frame_release", "vr_peer_frame_status",
     "vr_upload_synthetic", "vr_synthetic_to_host",
@@ -107,6 +107,7 @@ def lib():
         L.vr_owned_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.vr_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_read_frame.argtypes = [C.c_void_p, C.c_void_p]
+        L.vr_render_owned_to_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_assemble_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vr_read_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -252,6 +253,12 @@ class Context:
     def render_to_host_ptr(self, host_ptr: int):
         st = RenderStats()
         _check(lib().vr_render(self._h, C.c_void_p(host_ptr), C.byref(st)))
+        return st
+
+    def render_owned_to_host_ptr(self, host_full_frame_ptr: int):
+        """This rank's row tiles into their rows of a full host frame (shared by all ranks)."""
+        st = RenderStats()
+        _check(lib().vr_render_owned_to_host(self._h, C.c_void_p(host_full_frame_ptr), C.byref(st)))
         return st
 
     def render_device(self, dptr: int, compact: bool = False, stream: int = 0):

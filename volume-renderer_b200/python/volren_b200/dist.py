@@ -5,7 +5,10 @@ followed by the tile de-interleave.  No other collective touches the data path."
 from __future__ import annotations
 
 import os
+import time
+from multiprocessing import shared_memory
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -77,3 +80,76 @@ def assemble_reference(gathered: torch.Tensor, height: int, tile_rows: int) -> t
     rank = tile % world
     local = (tile // world) * tile_rows + (ys % tile_rows)
     return gathered[rank, local]
+
+
+class SharedHostFrame:
+    """One W x H RGBA32F frame in POSIX shared memory, mapped by every rank process (one process per
+    GPU) and page-locked in each with cudaHostRegister, so that every rank copies its own row tiles
+    device->host over its own PCIe link (vr_render_owned_to_host).  Two tiny flag arrays in the same
+    segment order the hand-off without any collective: done[r] = last frame rank r has fully written,
+    released = last frame the consumer (rank 0) is finished with.  x86 total store order + the stream
+    synchronisation inside vr_render_owned_to_host make plain stores sufficient."""
+
+    HEADER = 4096       # bytes: int64 done[world] at 0, int64 released at 2048
+
+    def __init__(self, name: str, width: int, height: int, rank: int, world: int, create: bool, register_cuda: bool = True):
+        self.rank, self.world, self.W, self.H = rank, world, width, height
+        nbytes = self.HEADER + width * height * 16
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        self.created = create
+        if not create:
+            # the creator owns the name: keep this process's resource tracker from unlinking it at exit
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        buf = np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf)
+        self.done = buf[:8 * world].view(np.int64)
+        self.released = buf[2048:2056].view(np.int64)
+        self.frame = buf[self.HEADER:].view(np.float32).reshape(height, width, 4)
+        if create:
+            self.done[:] = 0
+            self.released[:] = 0
+        self.registered = False
+        if register_cuda:
+            rc = torch.cuda.cudart().cudaHostRegister(self.frame.ctypes.data, width * height * 16, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+            self.registered = True
+
+    @property
+    def frame_ptr(self) -> int:
+        return self.frame.ctypes.data
+
+    def wait_released(self, frame_no: int, timeout_s: float = 10.0):
+        """Producer side: the consumer is finished with frame `frame_no` (the buffer may be overwritten)."""
+        t0 = time.perf_counter()
+        while int(self.released[0]) < frame_no:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"rank {self.rank}: frame {frame_no} was never released")
+
+    def mark_done(self, frame_no: int):
+        self.done[self.rank] = frame_no
+
+    def wait_all_done(self, frame_no: int, timeout_s: float = 10.0):
+        """Consumer side: every rank has written its rows of frame `frame_no`."""
+        t0 = time.perf_counter()
+        while int(self.done.min()) < frame_no:
+            if time.perf_counter() - t0 > timeout_s:
+                raise TimeoutError(f"frame {frame_no}: done flags {self.done.tolist()}")
+
+    def release(self, frame_no: int):
+        self.released[0] = frame_no
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.frame.ctypes.data)
+            self.registered = False
+        self.done = self.released = self.frame = None
+        try:
+            self.shm.close()
+            if self.created:
+                self.shm.unlink()
+        except Exception:
+            pass
