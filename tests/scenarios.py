@@ -85,6 +85,8 @@ CASES = [
     ("window_min_gt_max", "mix64_u8", "K0", (64, 64), dict(alpha_scale=0.001, min_val=200, max_val=100, filter=1)),
     ("const_closed_form", "const_u8", "K0", (96, 96), dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)),
     ("one_voxel", "one_voxel_u8", "K0", (64, 64), dict(alpha_scale=0.7, min_val=0, max_val=255, filter=1)),
+    # VolumeRenderer.cs:115: the loop stops after 10000 samples (16 voxels / (step 1/16 * 0.001) = 16000 > 10000)
+    ("iteration_cap_10000", "const_u8", "K0", (48, 48), dict(alpha_scale=0.00001, min_val=0, max_val=255, filter=1, step_scale=0.001)),
     ("half_step_opacity_corrected", "smooth64_u8", "K1", (128, 128), dict(alpha_scale=0.1, min_val=0, max_val=255, filter=1, step_scale=0.5, opacity_correction=1)),
 ]
 
