@@ -76,33 +76,48 @@ bool readRawPayload(const std::string& raw_fn, uint64_t n, std::vector<uint8_t>&
 
 namespace {
 
-// MSB-first bit source over a byte buffer; reads past the end yield zero bits (the reference
-// pads its cache with a zero word).
+// MSB-first bit source over a byte buffer with a 64-bit accumulator (left aligned).  Reads past
+// the end yield zero bits (the reference pads its cache with a zero word).
 class BitSource {
 public:
     BitSource(const uint8_t* p, uint64_t n) : p_(p), n_(n) {}
-    uint32_t take(unsigned nbits)
+    // nbits <= 32
+    inline uint32_t take(unsigned nbits)
     {
-        uint32_t v = 0;
-        while (nbits) {
-            if (avail_ == 0) {
-                cur_ = pos_ < n_ ? p_[pos_] : 0;
-                ++pos_;
-                avail_ = 8;
-            }
-            const unsigned k = nbits < avail_ ? nbits : avail_;
-            v = (v << k) | ((cur_ >> (avail_ - k)) & ((1u << k) - 1u));
-            avail_ -= k;
-            nbits -= k;
-        }
+        if (nbits == 0) return 0;
+        if (avail_ < nbits) refill();
+        const uint32_t v = (uint32_t)(acc_ >> (64 - nbits));
+        acc_ <<= nbits;
+        avail_ -= nbits;
         return v;
     }
-    // true once every real byte has been consumed and we are only returning padding
-    bool exhausted() const { return pos_ > n_ + 4; }
+    // true once more than four bytes of padding have been consumed: the stream has no end marker
+    bool exhausted() const { return pos_ * 8 - avail_ > (n_ + 4) * 8; }
 private:
+    inline void refill()
+    {
+        if (pos_ + 8 <= n_) {
+            // eight bytes at once, big endian; keep what fits behind the bits still pending
+            uint64_t w;
+            std::memcpy(&w, p_ + pos_, 8);
+            w = __builtin_bswap64(w);
+            const unsigned take_bytes = (64 - avail_) >> 3;
+            if (take_bytes == 8) acc_ = w;                       // avail_ == 0: a 64-bit shift would be undefined
+            else acc_ |= (w >> avail_) & ~((1ull << (64 - avail_ - 8 * take_bytes)) - 1ull);
+            pos_ += take_bytes;
+            avail_ += 8 * take_bytes;
+            return;
+        }
+        while (avail_ <= 56) {
+            const uint64_t b = pos_ < n_ ? p_[pos_] : 0;
+            ++pos_;
+            acc_ |= b << (56 - avail_);
+            avail_ += 8;
+        }
+    }
     const uint8_t* p_;
     uint64_t n_, pos_ = 0;
-    uint32_t cur_ = 0;
+    uint64_t acc_ = 0;
     unsigned avail_ = 0;
 };
 
@@ -116,22 +131,35 @@ void weaveChannels(std::vector<uint8_t>& data, uint32_t channels, uint64_t block
     for (uint64_t base = 0; base < total; base += span) {
         const uint64_t len = (total - base < span) ? total - base : span;
         tmp.assign(data.begin() + (std::ptrdiff_t)base, data.begin() + (std::ptrdiff_t)(base + len));
-        uint64_t src = 0;
-        for (uint32_t c = 0; c < channels; ++c)
-            for (uint64_t j = c; j < len; j += channels) data[base + j] = tmp[src++];
+        uint8_t* d = data.data() + base;
+        if (channels == 2 && (len & 1) == 0) {
+            // 16-bit volumes: the two byte planes of the block, zipped
+            const uint8_t* lo = tmp.data();
+            const uint8_t* hi = tmp.data() + len / 2;
+            for (uint64_t j = 0; j < len / 2; ++j) { d[2 * j] = lo[j]; d[2 * j + 1] = hi[j]; }
+        } else {
+            uint64_t src = 0;
+            for (uint32_t c = 0; c < channels; ++c)
+                for (uint64_t j = c; j < len; j += channels) d[j] = tmp[src++];
+        }
         if (span == total) break;
     }
 }
 
 }  // namespace
 
+// The bit stream is sequential by construction (every value is a delta on the previous one), so the
+// decoder is one tight loop: runs of `run` values share a bit width; after the first `row` values the
+// delta is additionally predicted from the previous row (ddsbase.cpp:394-452 of the reference).
 bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<uint8_t>& out, std::string& error)
 {
     BitSource bits(chunk, size);
     const uint32_t channels = bits.take(2) + 1;     // "skip"
     const uint32_t row = bits.take(16) + 1;         // "strip": predictor distance
-    out.clear();
-    out.reserve(size * 2);
+    uint64_t cap = size * 2 + 4096;
+    out.resize(cap);
+    uint8_t* o = out.data();
+    uint64_t n = 0;
     int value = 0;
     for (;;) {
         const uint32_t run = bits.take(7);
@@ -139,15 +167,33 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
         const uint32_t code = bits.take(3);
         const unsigned width = code ? code + 1 : 0;
         const int bias = (int)((1u << width) >> 1);
-        for (uint32_t k = 0; k < run; ++k) {
-            int delta = (int)bits.take(width) - bias;
-            const uint64_t n = out.size();
-            if (row != 1 && n > row) delta += (int)out[n - row] - (int)out[n - row - 1];
-            value = (value + delta) & 0xff;         // wrap into 0..255
-            out.push_back((uint8_t)value);
+        if (n + run > cap) {
+            cap = cap * 2 + run;
+            out.resize(cap);
+            o = out.data();
+        }
+        uint32_t k = 0;
+        if (row != 1) {
+            // the predictor needs row + 1 values of history
+            for (; k < run && n <= row; ++k) {
+                value = (value + (int)bits.take(width) - bias) & 0xff;
+                o[n++] = (uint8_t)value;
+            }
+            const uint8_t* h = o + n - row;          // h[0] = value one row back, h[-1] = its predecessor
+            for (; k < run; ++k, ++h) {
+                const int delta = (int)bits.take(width) - bias + (int)h[0] - (int)h[-1];
+                value = (value + delta) & 0xff;      // wrap into 0..255
+                o[n++] = (uint8_t)value;
+            }
+        } else {
+            for (; k < run; ++k) {
+                value = (value + (int)bits.take(width) - bias) & 0xff;
+                o[n++] = (uint8_t)value;
+            }
         }
         if (bits.exhausted()) { error = "DDS stream: missing end-of-stream marker"; return false; }
     }
+    out.resize(n);
     weaveChannels(out, channels, block);
     return true;
 }
