@@ -181,7 +181,8 @@ VR_API int vr_frame_close_ipc(vr_context* ctx, float* d_peer_frame);
  *            bounded spin until all `world` ranks have arrived -> the frame is complete on the stream.
  *   release: owner, after consuming frame `frame_no`: publishes it; other ranks, before rendering
  *            frame_no + 1: bounded spin on the owner's word over NVLink.
- * Spins give up after 5 s and set the timed_out word (vr_peer_frame_status); they never hang the GPU. */
+ * Spins give up after 5 s (VR_PEER_TIMEOUT_MS overrides, e.g. when rank processes time-share one GPU) and set
+ * the timed_out word (vr_peer_frame_status); they never hang the GPU. */
 VR_API int vr_peer_frame_arrive(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int world,
                                 int is_owner, void* cuda_stream);
 VR_API int vr_peer_frame_release(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int is_owner,

@@ -330,3 +330,26 @@ def test_owned_tiles_to_host_frame_assemble_the_frame(world, tile_rows):
             # rows of other ranks are untouched
             assert np.array_equal(host[~owned].view(np.uint32), before[~owned].view(np.uint32))
     assert np.array_equal(host.view(np.uint32), full.view(np.uint32))
+
+
+@pytest.mark.parametrize("vname,cname,kw", [
+    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=0, max_val=255, filter=1, view_top=1)),
+    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1, view_bottom=1)),
+    ("mix_64x64x32_u16", "K2", dict(alpha_scale=0.05, min_val=1000, max_val=3000, filter=1, view_top=1)),
+    ("mix64_u8", "K1", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1, view_bottom=1, step_scale=0.5)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1, view_top=1, view_bottom=1)),   # top wins (:183)
+])
+def test_view_swizzles_run_on_the_pipelined_gather_kernel(vname, cname, kw):
+    """rotate_to_top / rotate_to_bottom (VolumeRenderer.cs:68-78,183-190) with the trilinear filter run
+    in the optimised kernel and equal the oracle and the generic DIRECT loop bit for bit."""
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    cam = scenarios.camera(cname)
+    W, H = 320, 200
+    okw, vkw = scenarios.split_kwargs(kw)
+    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
+    img, st = run_product(vox, dims, vs, cam, W, H, vkw)
+    assert st.kernel_used == vb.KERNEL_TEXPAIR_PIPE
+    compare(img, ref, f"view {vname}/{cname}")
+    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
+    assert st2.kernel_used == vb.KERNEL_DIRECT
+    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))

@@ -71,6 +71,9 @@ def _worker_device_barrier(rank, world, port, out_path):
     """Several frames back to back with NO host-side collective between them: completion and reuse of
     rank 0's frame are ordered only by the barrier words in peer memory (vr_peer_frame_arrive/release)."""
     sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    # the rank processes of this test may time-share one GPU (a spinning wait kernel then holds its whole
+    # time slice while the kernel it waits for sits in another process): give the spins a generous bound
+    os.environ["VR_PEER_TIMEOUT_MS"] = "60000"
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import volren_b200 as vb
@@ -104,11 +107,14 @@ def _worker_device_barrier(rank, world, port, out_path):
                 got = ctx.read_frame()                               # same stream: after the arrival wait
                 if not np.array_equal(got.view(np.uint32), refs[f - 1].view(np.uint32)):
                     ok = 0
+                    print(f"frame {f}: {int((got.view(np.uint32) != refs[f - 1].view(np.uint32)).any(axis=(1, 2)).sum())} rows differ, "
+                          f"status {ctx.peer_frame_status(ptr)}", flush=True)
                 ctx.peer_frame_release(ptr, f, is_owner=True)
         if rank == 0:
             st = ctx.peer_frame_status(ptr)
             if st["timed_out"] or st["arrivals"] != frames * world or st["released"] != frames:
                 ok = 0
+                print(f"barrier status {st}, expected {frames * world} arrivals, {frames} released", flush=True)
             np.save(out_path, np.array([ok]))
         dist.barrier()
         if rank != 0:

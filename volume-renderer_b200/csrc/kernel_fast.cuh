@@ -739,8 +739,10 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, cudaTex
 enum { FETCH_TEX = 0, FETCH_LSU = 1 };
 // MODE: MODE_DVR = rayMarchVolume (:104-139); MODE_TF = the same with the transfer-function extension
 // (SURVEY 8a-7): src.a = lut[floor(v*255 + 0.5)], rgb stays v; MODE_MIP = MIP (:141-173): dest = max over
-// the samples of v*alpha_scale, with the inherited `dest.a >= 0.95` exit of :156.
-enum { MODE_DVR = 0, MODE_TF = 1, MODE_MIP = 2 };
+// the samples of v*alpha_scale, with the inherited `dest.a >= 0.95` exit of :156; MODE_DVR_TOP / _BOTTOM =
+// DVR with the view_top / view_bottom tex-coord swizzle of cartesianToTextureCoord (:183-190; the host
+// builds the bounding box from the .xzy-swizzled dims and spacing, :68-78).
+enum { MODE_DVR = 0, MODE_TF = 1, MODE_MIP = 2, MODE_DVR_TOP = 3, MODE_DVR_BOTTOM = 4 };
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FA = FETCH_TEX, int FB = FETCH_TEX, int MODE = MODE_DVR>
 __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, const TexArgs& args,
                                                        const float pos0[3], const float dstep[3], float& outC, float& outA,
@@ -775,7 +777,14 @@ __device__ __forceinline__ void march_ray_texpair_pipe(const FrameConsts& fc, co
             txy = ffma(r, ixy, q0);
             tzq = div_by<DIV_MARKSTEIN>(qz, fc.denom[2], fc.inv_denom[2]);
         }
-        tz = __fsub_rn(1.0f, tzq);
+        tz = __fsub_rn(1.0f, tzq);                                      // :180
+        if (MODE == MODE_DVR_TOP) {                                     // :183-186  (x, 1 - z, y), z already flipped
+            const float ty = __fsub_rn(1.0f, tz), qy = hi(txy);
+            txy = mk2(lo(txy), ty); tz = qy;
+        } else if (MODE == MODE_DVR_BOTTOM) {                           // :187-190  (x, z, 1 - y)
+            const float ty = tz, qy = hi(txy);
+            txy = mk2(lo(txy), ty); tz = __fsub_rn(1.0f, qy);
+        }
         return max(max(__float_as_uint(lo(txy)), __float_as_uint(hi(txy))), __float_as_uint(tz));
     };
 

@@ -171,8 +171,11 @@ int make_plan(vr_context* c, int compact, LaunchPlan* plan)
                          (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
     const bool pipe_selectable = c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
                                  (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
-    const bool mip_fast = p.is_mip == 1 && p.use_tf == 0 && pipe_selectable;      // ... and a MIP form
-    bool generic = (p.is_mip == 1 && !mip_fast) || (p.use_tf != 0 && !(tf_fast && p.is_mip != 1)) || p.view_top == 1 || p.view_bottom == 1 ||
+    const bool mip_fast = p.is_mip == 1 && p.use_tf == 0 && p.view_top != 1 && p.view_bottom != 1 && pipe_selectable;   // ... a MIP form
+    const bool swizzled = p.view_top == 1 || p.view_bottom == 1;
+    const bool view_fast = swizzled && p.is_mip != 1 && p.use_tf == 0 && pipe_selectable;   // ... and view_top / view_bottom forms
+    bool generic = (p.is_mip == 1 && !mip_fast) || (p.use_tf != 0 && !(tf_fast && p.is_mip != 1 && !swizzled)) ||
+                   (swizzled && !view_fast) ||
                    fc.opacity_correction || !(p.max_val > p.min_val);
     if (!generic) {
         bool ok = false;
@@ -365,6 +368,8 @@ int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cud
 {
     if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
     if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
+    if (plan.fc.view_top)           return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR_TOP>(c, plan, d_out, s, win);
+    if (plan.fc.view_bottom)        return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR_BOTTOM>(c, plan, d_out, s, win);
     if (plan.fc.is_mip)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_MIP>(c, plan, d_out, s, win);
     if (plan.fc.use_tf)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_TF>(c, plan, d_out, s, win);
     return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR>(c, plan, d_out, s, win);
@@ -460,7 +465,7 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
     int want = c->params.kernel;
-    if ((fc.use_tf || fc.is_mip) && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
+    if ((fc.use_tf || fc.is_mip || fc.view_top || fc.view_bottom) && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
     if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
     if ((want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) && !zlin_ok) want = VR_KERNEL_TEXPAIR_PIPE;
@@ -1055,6 +1060,18 @@ int vr_frame_close_ipc(vr_context* c, float* d_peer_frame)
     return VR_OK;
 }
 
+// bound of the barrier spins: 5 s by default (a frame takes milliseconds); VR_PEER_TIMEOUT_MS overrides it,
+// e.g. for rank processes that time-share ONE GPU, where a spinning wait kernel holds its whole time slice
+static unsigned long long peer_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char* e = std::getenv("VR_PEER_TIMEOUT_MS");
+        const long long ms = e ? std::atoll(e) : 5000;
+        return (unsigned long long)(ms > 0 ? ms : 5000) * 1000000ull;
+    }();
+    return ns;
+}
+
 // the barrier words live behind the pixels of the frame `d_target_frame` points to (same W x H on every rank)
 static unsigned int* frame_sync_words(const vr_context* c, float* d_target_frame)
 {
@@ -1068,7 +1085,7 @@ int vr_peer_frame_arrive(vr_context* c, float* d_target_frame, uint32_t frame_no
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
     unsigned int* sync = frame_sync_words(c, d_target_frame);
     vr::peer_signal_kernel<<<1, 1, 0, s>>>(sync);
-    if (is_owner) vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, 5000000000ull);
+    if (is_owner) vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, peer_timeout_ns());
     VR_CUDA(cudaGetLastError());
     return VR_OK;
 }
@@ -1080,7 +1097,7 @@ int vr_peer_frame_release(vr_context* c, float* d_target_frame, uint32_t frame_n
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
     unsigned int* sync = frame_sync_words(c, d_target_frame);
     if (is_owner) vr::peer_release_kernel<<<1, 1, 0, s>>>(sync, frame_no);
-    else          vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 1, frame_no, 5000000000ull);
+    else          vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 1, frame_no, peer_timeout_ns());
     VR_CUDA(cudaGetLastError());
     return VR_OK;
 }
