@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--camera", default="K2", choices=["K0", "K1", "K2"])
     ap.add_argument("--alpha", type=float, default=0.02)
     ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu", "nearest_tex"])
     ap.add_argument("--cpu-row-stride", type=int, default=1, help="cpu_baseline renders every n-th row")
     ap.add_argument("--mip", action="store_true", help="maximum-intensity projection (the reference's use_mip toggle)")
     ap.add_argument("--tf", action="store_true", help="CubicSpline transfer function (default alpha knots of the reference's TF editor)")
@@ -229,7 +229,7 @@ def run_ours(args):
     dims, bpv = cfg["dims"], cfg["bpv"]
     cam = workloads.camera_block(args.camera)
     kernel = {"auto": vb.KERNEL_AUTO, "direct": vb.KERNEL_DIRECT, "windowed": vb.KERNEL_WINDOWED, "fast": vb.KERNEL_FAST, "texgather": vb.KERNEL_TEXGATHER,
-              "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "hybrid": vb.KERNEL_HYBRID, "zlsu": vb.KERNEL_ZLSU}[args.kernel]
+              "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "hybrid": vb.KERNEL_HYBRID, "zlsu": vb.KERNEL_ZLSU, "nearest_tex": vb.KERNEL_NEAREST_TEX}[args.kernel]
     params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
                                filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
                                step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None,
@@ -360,7 +360,10 @@ def run_ours(args):
                 else "hand-off to rank 0 on the device, rank 0 copies the frame to the host")
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:                  # the end-to-end path warms up like the device path (first-call
+            barrier()                         # stream/event creation, first copies into the pinned frame)
+            t0 = time.perf_counter()
         ctx.set_camera(cam)
         ctx.set_params(params)
         if world == 1:
@@ -451,7 +454,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel", 3: "march_packed_kernel" if args.filter == "trilinear" else "march_fast_kernel", 4: "march_texgather_kernel",
-                                                    5: "march_texpair_kernel", 6: "march_texpair2_kernel", 7: "march_texpair_pipe_kernel", 8: "march_texpair_pipe_kernel", 9: "march_texpair_pipe_kernel"}.get(used[0], "?"),
+                                                    5: "march_texpair_kernel", 6: "march_texpair2_kernel", 7: "march_texpair_pipe_kernel", 8: "march_texpair_pipe_kernel", 9: "march_texpair_pipe_kernel", 10: "march_nearest_tex_kernel"}.get(used[0], "?"),
             "kernel_ms_avg": avg_kernel_ms}
     if counted is not None:
         owned_px = sum(min(TILE_ROWS, H - t0_ * TILE_ROWS) for t0_ in range(rank, (H + TILE_ROWS - 1) // TILE_ROWS, world)) * W

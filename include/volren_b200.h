@@ -56,11 +56,13 @@ enum { VR_FILTER_NEAREST = 0, VR_FILTER_TRILINEAR = 1 };
  *            TEXPAIR_PIPE: software-pipelined, two gathers in flight per warp;
  *            HYBRID: same pipeline, even samples through the texture unit, odd samples through the
  *            LSU (ld.global.nc of the same z-pair words from a linear copy); ZLSU: LSU only
+ *   NEAREST_TEX nearest filter only: one integer-coordinate texel load (TLD) per sample from the
+ *            source-type layered array, software pipelined
  *   AUTO     the fastest kernel that covers the frame's parameters
  * A request the frame's parameters do not allow falls back (TEXPAIR -> TEXGATHER/WINDOWED -> FAST -> DIRECT). */
 enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2, VR_KERNEL_FAST = 3, VR_KERNEL_TEXGATHER = 4,
        VR_KERNEL_TEXPAIR = 5, VR_KERNEL_TEXPAIR2 = 6, VR_KERNEL_TEXPAIR_PIPE = 7,
-       VR_KERNEL_HYBRID = 8, VR_KERNEL_ZLSU = 9 };
+       VR_KERNEL_HYBRID = 8, VR_KERNEL_ZLSU = 9, VR_KERNEL_NEAREST_TEX = 10 };
 
 typedef struct vr_context vr_context;
 

@@ -27,8 +27,10 @@ def run_product(vox, dims, voxel_size, cam, W, H, vkw, kernel=vb.KERNEL_AUTO, pa
 
 @pytest.mark.parametrize("cid", [c[0] for c in scenarios.CASES])
 @pytest.mark.parametrize("kernel", [vb.KERNEL_DIRECT, vb.KERNEL_AUTO, vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER,
-                                    vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU],
-                         ids=["direct", "auto", "fast", "windowed", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu"])
+                                    vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU,
+                                    vb.KERNEL_NEAREST_TEX],
+                         ids=["direct", "auto", "fast", "windowed", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu",
+                              "nearest_tex"])
 def test_case_matches_oracle(cid, kernel):
     _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
     vox, dims, bpv, vs = scenarios.volume(vname)
@@ -353,3 +355,28 @@ def test_view_swizzles_run_on_the_pipelined_gather_kernel(vname, cname, kw):
     direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
     assert st2.kernel_used == vb.KERNEL_DIRECT
     assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
+
+
+@pytest.mark.parametrize("vname,cname,kw", [
+    ("mix64_u8", "K0", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=0)),
+    ("mix64_u8", "K2", dict(alpha_scale=1.0, min_val=40, max_val=200, filter=0)),
+    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=10, max_val=250, filter=0)),
+    ("mix_64x64x32_u16", "K0", dict(alpha_scale=0.5, min_val=1000, max_val=3000, filter=0)),
+    ("rand_40x56x33_u16", "orbit", dict(alpha_scale=0.03, min_val=0, max_val=4095, filter=0, step_scale=0.5)),
+    ("full_u16", "K1", dict(alpha_scale=0.04, min_val=0, max_val=65535, filter=0)),
+    ("one_voxel_u8", "K0", dict(alpha_scale=0.7, min_val=0, max_val=255, filter=0)),
+])
+def test_nearest_filter_runs_on_the_texel_load_kernel(vname, cname, kw):
+    """The de-facto reference filter (integer texture => nearest texel): AUTO runs the pipelined
+    texel-load kernel, bit-identical to the oracle and to the FAST and DIRECT kernels."""
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    cam = scenarios.camera(cname)
+    W, H = 320, 200
+    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
+    img, st = run_product(vox, dims, vs, cam, W, H, kw)
+    assert st.kernel_used == vb.KERNEL_NEAREST_TEX
+    compare(img, ref, f"nearest {vname}/{cname}")
+    for kernel in (vb.KERNEL_FAST, vb.KERNEL_DIRECT):
+        other, st2 = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
+        assert st2.kernel_used == kernel
+        assert np.array_equal(other.view(np.uint32), img.view(np.uint32))

@@ -890,6 +890,118 @@ march_texpair_pipe_kernel(const __grid_constant__ FrameConsts fc, const __grid_c
     reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
 }
 
+// ------------------------------------------------------------------------------------------
+// Nearest-filter march (what an integer texture with GL_LINEAR does on NVIDIA drivers, i.e. the
+// reference's de-facto output): one texel per sample, fetched with an integer-coordinate texel load
+// (`tex.a2d ... .s32` -> SASS TLD.LZ, one component returned) from the source-type layered array.
+// i = clamp(floor(u * N), 0, N-1) per axis (VolumeRenderer.cs:121 + GL_CLAMP_TO_EDGE): the clamp is an
+// unsigned min, which also makes the look-ahead fetch of the software pipeline safe when sample i+1
+// lies outside the box.  Same ping-pong pipeline as march_ray_texpair_pipe (two loads in flight per warp).
+__device__ __forceinline__ uint32_t tld_layer(cudaTextureObject_t tex, unsigned layer, unsigned x, unsigned y)
+{
+    uint32_t r, g, b, a;
+    asm volatile("tex.a2d.v4.u32.s32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                 : "=r"(r), "=r"(g), "=r"(b), "=r"(a) : "l"(tex), "r"(layer), "r"(x), "r"(y));
+    return r;
+}
+
+template <int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__device__ __forceinline__ void march_ray_nearest_tex(const FrameConsts& fc, cudaTextureObject_t tex,
+                                                      const float pos0[3], const float dstep[3], float& outC, float& outA)
+{
+    f2 pxy = mk2(pos0[0], pos0[1]);
+    float pz = pos0[2];
+    const f2 dxy = mk2(dstep[0], dstep[1]);
+    const float dz = dstep[2];
+    const f2 hxy = mk2(fc.half_len[0], fc.half_len[1]);
+    const float hz = fc.half_len[2];
+    const f2 ixy = mk2(fc.inv_denom[0], fc.inv_denom[1]);
+    const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
+    const float nz = fc.dimf[2];
+    const unsigned mx = (unsigned)fc.dim[0] - 1u, my = (unsigned)fc.dim[1] - 1u, mz = (unsigned)fc.dim[2] - 1u;
+    float C = outC, A = outA;
+
+    auto tex_coord_key = [&](f2& txy, float& tz) -> unsigned {       // cartesianToTextureCoord :175-192
+        const f2 qxy = fadd(pxy, hxy);
+        const float qz = __fadd_rn(pz, hz);
+        float tzq;
+        if (UNIT) { txy = qxy; tzq = qz; }
+        else if (TCDIV == DIV_RECIP_EXACT) { txy = fmul(qxy, ixy); tzq = __fmul_rn(qz, fc.inv_denom[2]); }
+        else {
+            const f2 q0 = fmul(qxy, ixy);
+            const f2 r = ffma(mk2(-fc.denom[0], -fc.denom[1]), q0, qxy);
+            txy = ffma(r, ixy, q0);
+            tzq = div_by<DIV_MARKSTEIN>(qz, fc.denom[2], fc.inv_denom[2]);
+        }
+        tz = __fsub_rn(1.0f, tzq);
+        return max(max(__float_as_uint(lo(txy)), __float_as_uint(hi(txy))), __float_as_uint(tz));
+    };
+    auto fetch = [&](f2 txy, float tz) -> uint32_t {
+        const f2 uxy = fmul(txy, nxy);
+        const float uz = __fmul_rn(tz, nz);
+        const unsigned ix = min((unsigned)__float2int_rd(lo(uxy)), mx);
+        const unsigned iy = min((unsigned)__float2int_rd(hi(uxy)), my);
+        const unsigned iz = min((unsigned)__float2int_rd(uz), mz);
+        return tld_layer(tex, iz, ix, iy);
+    };
+    auto consume = [&](uint32_t texel) {                               // :121-132
+        const float s = __fsub_rn(__uint_as_float(0x4B000000u | texel), 8388608.0f);
+        float v;
+        if (WIN == WIN_COVERS0) v = div_by<DIV_MARKSTEIN>(s, fc.frange, fc.inv_frange);
+        else v = div_by<DIV_MARKSTEIN>(__fsub_rn(fminf(fmaxf(s, fc.fmin), fc.fmax), fc.fmin), fc.frange, fc.inv_frange);
+        const float a = __fmul_rn(v, fc.alpha_scale);
+        const float c = __fmul_rn(v, a);
+        const float t = __fsub_rn(1.0f, A);
+        const f2 ca_t = fmul(mk2(c, a), splat2(t));
+        C = __fadd_rn(C, lo(ca_t));
+        A = __fadd_rn(A, hi(ca_t));
+    };
+    auto stage = [&](uint32_t cur, uint32_t& nxt) -> bool {
+        pxy = fadd(pxy, dxy);                                          // :136
+        pz = __fadd_rn(pz, dz);
+        f2 txy; float tz;
+        const bool inside_n = tex_coord_key(txy, tz) <= 0x3F800000u;   // :118 of sample i+1
+        nxt = fetch(txy, tz);
+        consume(cur);
+        return inside_n && __float_as_uint(A) < 0x3F733333u;
+    };
+
+    f2 txy; float tz;
+    if (tex_coord_key(txy, tz) > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return;   // :118, first sample
+    uint32_t ta = fetch(txy, tz), tb = 0;
+    for (int iter = 0; NOCAP || iter < 10000; iter += 2) {
+        if (!stage(ta, tb)) break;
+        if (!NOCAP && iter + 1 >= 10000) break;
+        if (!stage(tb, ta)) break;
+    }
+    outC = C; outA = A;
+}
+
+template <int TCDIV, int WIN, bool UNIT, bool NOCAP>
+__global__ void __launch_bounds__(256, NOCAP ? 8 : 6)
+march_nearest_tex_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ TexArgs args)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int lrow = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (px >= fc.W || lrow >= args.local_rows) return;
+    const int py = owned_row_to_global(fc, lrow);
+    if (py >= fc.H) return;
+    const RaySetup r = setup_ray(fc, px, py);
+    float C = 0.0f, A = 0.0f;
+    if (r.hit) {
+        float pos[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            pos[i] = __fadd_rn(__fadd_rn(r.org[i], __fmul_rn(r.dir[i], r.t_min)), __fmul_rn(r.dir[i], 0.000001f));
+            ds[i] = __fmul_rn(r.dir[i], fc.step);
+        }
+        march_ray_nearest_tex<TCDIV, WIN, UNIT, NOCAP>(fc, args.tex, pos, ds, C, A);
+    }
+    const int orow = fc.compact ? lrow : py;
+    reinterpret_cast<float4*>(args.out)[(size_t)orow * fc.W + px] = make_float4(C, C, C, A);
+}
+
 // Two rays (horizontally adjacent pixels) per thread over the same z-pair array: every IEEE
 // operation of the sample -- position, tex-coord, texel coordinate, weights, the seven lerps,
 // window, compositing products -- is issued ONCE as a packed f32x2 instruction for both rays

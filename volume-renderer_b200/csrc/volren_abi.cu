@@ -287,6 +287,32 @@ int launch_texgather(vr_context* c, const LaunchPlan& plan, float* d_out, cudaSt
     return VR_OK;
 }
 
+template <int WIN>
+void launch_nearest_tex_w(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+{
+    using namespace vr;
+    const dim3 block(256);
+    if (unit && nocap)        march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip && nocap)  march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else if (recip)           march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+    else if (nocap)           march_nearest_tex_kernel<DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
+    else                      march_nearest_tex_kernel<DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
+}
+
+// nearest filter: integer-coordinate texel loads from the source-type layered array, software pipelined
+int launch_nearest_tex(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+{
+    vr::TexArgs a{};
+    a.tex = c->tex; a.out = d_out; a.local_rows = plan.local_rows;
+    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
+    bool unit, recip, nocap;
+    packed_flags(c, plan, &unit, &recip, &nocap);
+    if (win == vr::WIN_COVERS0) launch_nearest_tex_w<vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
+    else                        launch_nearest_tex_w<vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+    VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
 template <typename T, int WIN>
 void launch_texpair_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
 {
@@ -464,7 +490,10 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
                         ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
     const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
     const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
+    const bool nearest_tex_ok = base_ok && fc.filter == VR_FILTER_NEAREST && c->tex != 0;
     int want = c->params.kernel;
+    if (want == VR_KERNEL_NEAREST_TEX && !nearest_tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
+    if (want == VR_KERNEL_AUTO && nearest_tex_ok) want = VR_KERNEL_NEAREST_TEX;
     if ((fc.use_tf || fc.is_mip || fc.view_top || fc.view_bottom) && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
     if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
     const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
@@ -483,6 +512,10 @@ int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream
         // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
         cudaGetLastError();
         want = VR_KERNEL_FAST;
+    }
+    if (want == VR_KERNEL_NEAREST_TEX) {
+        *used = VR_KERNEL_NEAREST_TEX;
+        return launch_nearest_tex(c, plan, d_out, s, win);
     }
     if (want == VR_KERNEL_TEXPAIR_PIPE || want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) {
         *used = (uint32_t)want;
@@ -847,7 +880,7 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_ZLSU)
+    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_NEAREST_TEX)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
     if (p->use_tf) {
         // the optimised loop tests ranges on float bit patterns: it needs a finite, non-negative opacity LUT

@@ -20,7 +20,7 @@ HOST_LIB_PATH = os.path.join(LIB_DIR, "libvolren_host.so")
 
 FILTER_NEAREST, FILTER_TRILINEAR = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOWED, KERNEL_FAST, KERNEL_TEXGATHER, KERNEL_TEXPAIR, KERNEL_TEXPAIR2, KERNEL_TEXPAIR_PIPE = 0, 1, 2, 3, 4, 5, 6, 7
-KERNEL_HYBRID, KERNEL_ZLSU = 8, 9
+KERNEL_HYBRID, KERNEL_ZLSU, KERNEL_NEAREST_TEX = 8, 9, 10
 
 VR_OK = 0
 
