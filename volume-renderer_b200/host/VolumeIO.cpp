@@ -93,6 +93,16 @@ public:
     }
     // true once more than four bytes of padding have been consumed: the stream has no end marker
     bool exhausted() const { return pos_ * 8 - avail_ > (n_ + 4) * 8; }
+    // make at least 56 bits available, then hand out `nbits`-wide fields without further checks
+    inline void fill() { if (avail_ < 56) refill(); }
+    inline unsigned available() const { return avail_; }
+    inline uint32_t takeUnchecked(unsigned nbits)      // 1 <= nbits <= 8, caller guarantees availability
+    {
+        const uint32_t v = (uint32_t)(acc_ >> (64 - nbits));
+        acc_ <<= nbits;
+        avail_ -= nbits;
+        return v;
+    }
 private:
     inline void refill()
     {
@@ -162,9 +172,12 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
     uint64_t n = 0;
     int value = 0;
     for (;;) {
-        const uint32_t run = bits.take(7);
+        // run header: 7-bit count (0 = end of stream) + 3-bit width code.  Both fields in one read; when the
+        // count is zero the three extra bits belong to nothing (the stream ends there), so over-reading is harmless.
+        const uint32_t hdr = bits.take(10);
+        const uint32_t run = hdr >> 3;
         if (run == 0) break;
-        const uint32_t code = bits.take(3);
+        const uint32_t code = hdr & 7u;
         const unsigned width = code ? code + 1 : 0;
         const int bias = (int)((1u << width) >> 1);
         if (n + run > cap) {
@@ -173,26 +186,36 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
             o = out.data();
         }
         uint32_t k = 0;
-        if (row != 1) {
-            // the predictor needs row + 1 values of history
-            for (; k < run && n <= row; ++k) {
-                value = (value + (int)bits.take(width) - bias) & 0xff;
-                o[n++] = (uint8_t)value;
-            }
-            const uint8_t* h = o + n - row;          // h[0] = value one row back, h[-1] = its predecessor
-            for (; k < run; ++k, ++h) {
-                const int delta = (int)bits.take(width) - bias + (int)h[0] - (int)h[-1];
-                value = (value + delta) & 0xff;      // wrap into 0..255
-                o[n++] = (uint8_t)value;
-            }
-        } else {
-            for (; k < run; ++k) {
-                value = (value + (int)bits.take(width) - bias) & 0xff;
-                o[n++] = (uint8_t)value;
+        // values that have no predictor yet (or never: row == 1)
+        for (; k < run && (row == 1 || n <= row); ++k) {
+            value = (value + (int)bits.take(width) - bias) & 0xff;
+            o[n++] = (uint8_t)value;
+        }
+        if (k < run) {
+            // predicted values: delta += previous row's step.  h[0] = value one row back, h[-1] = its predecessor
+            const uint8_t* h = o + n - row;
+            if (width == 0) {
+                for (; k < run; ++k, ++h) {
+                    value = (value + (int)h[0] - (int)h[-1]) & 0xff;
+                    o[n++] = (uint8_t)value;
+                }
+            } else {
+                const unsigned per_fill = 56 / width;             // fields guaranteed after one fill()
+                while (k < run) {
+                    bits.fill();
+                    const uint32_t m = (run - k < per_fill) ? run - k : per_fill;
+                    for (uint32_t j = 0; j < m; ++j, ++h) {
+                        const int delta = (int)bits.takeUnchecked(width) - bias + (int)h[0] - (int)h[-1];
+                        value = (value + delta) & 0xff;           // wrap into 0..255
+                        o[n++] = (uint8_t)value;
+                    }
+                    k += m;
+                }
             }
         }
-        if (bits.exhausted()) { error = "DDS stream: missing end-of-stream marker"; return false; }
     }
+    // a stream without its end marker decodes zero padding until a zero count turns up: detect it here
+    if (bits.exhausted()) { error = "DDS stream: missing end-of-stream marker"; return false; }
     out.resize(n);
     weaveChannels(out, channels, block);
     return true;
