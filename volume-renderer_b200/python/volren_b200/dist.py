@@ -95,6 +95,16 @@ class SharedHostFrame:
     def __init__(self, name: str, width: int, height: int, rank: int, world: int, create: bool, register_cuda: bool = True):
         self.rank, self.world, self.W, self.H = rank, world, width, height
         nbytes = self.HEADER + width * height * 16
+        if create:
+            # a tmpfs that is too small lets shm_open/ftruncate/mmap succeed and then kills the process with
+            # SIGBUS on first touch: refuse up front (the caller falls back to rank 0 reading the frame back)
+            try:
+                st = os.statvfs("/dev/shm")
+                free = st.f_bavail * st.f_frsize
+            except OSError:
+                free = None
+            if free is not None and free < nbytes + (8 << 20):
+                raise RuntimeError(f"/dev/shm has {free >> 20} MiB free, the shared frame needs {nbytes >> 20} MiB")
         self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
         self.created = create
         if not create:
