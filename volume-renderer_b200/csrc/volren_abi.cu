@@ -992,7 +992,9 @@ int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
     const size_t bytes = (size_t)c->W * c->H * 4 * sizeof(float);
     // stateless kernels only (the windowed kernel keeps per-context scratch)
     static const bool no_bands = std::getenv("VR_NO_BANDS") != nullptr;
-    if (!no_bands && c->world == 1 && c->H >= 8 * vr_context::BANDS && c->params.kernel != VR_KERNEL_WINDOWED) {
+    // small frames copy in microseconds: four launches on four streams would cost more than they hide
+    const bool worth_banding = (size_t)c->W * c->H >= ((size_t)1 << 19);
+    if (!no_bands && worth_banding && c->world == 1 && c->H >= 8 * vr_context::BANDS && c->params.kernel != VR_KERNEL_WINDOWED) {
         int rc = render_banded(c, host_rgba, stats);
         if (rc != VR_OK) return rc;
         if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
