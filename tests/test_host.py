@@ -195,3 +195,23 @@ def test_png_bmp_ppm_writers(tmp_path):
         rows = np.frombuffer(raw[54:], np.uint8).reshape(h, stride)[:, :w * 3].reshape(h, w, 3)
         assert np.array_equal(rows[::-1, :, ::-1], img)      # bottom-up, BGR
     assert not host.write_image(str(tmp_path / "a.jpg"), ".jpg", img)
+
+
+def test_headless_example_compiles_against_the_host_mirror(tmp_path):
+    """examples/headless_render.cpp drives RendererCore / Camera with the reference GUI's call sequence;
+    it must compile and link with the host sources built into the application.
+    Without a GPU it fails the way the reference does when its framebuffer is incomplete: a runtime_error
+    caught in main, exit status 1."""
+    import subprocess
+    import volren_b200 as vb
+    root = vb.REPO_ROOT
+    h = os.path.join(root, "volume-renderer_b200", "host")
+    exe = str(tmp_path / "headless_render")
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I" + os.path.join(root, "include"), "-I" + h,
+           os.path.join(root, "examples", "headless_render.cpp")] + \
+          [os.path.join(h, f) for f in ("RendererCore.cpp", "Camera.cpp", "CubicSpline.cpp", "VolumeIO.cpp", "ImageIO.cpp")] + \
+          ["-L" + vb.LIB_DIR, "-lvolren_b200", "-Wl,-rpath," + vb.LIB_DIR, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 2 and "usage:" in run.stderr
