@@ -194,7 +194,7 @@ def test_png_bmp_ppm_writers(tmp_path):
         stride = (w * 3 + 3) & ~3
         rows = np.frombuffer(raw[54:], np.uint8).reshape(h, stride)[:, :w * 3].reshape(h, w, 3)
         assert np.array_equal(rows[::-1, :, ::-1], img)      # bottom-up, BGR
-    assert not host.write_image(str(tmp_path / "a.jpg"), ".jpg", img)
+    assert not host.write_image(str(tmp_path / "a.tga"), ".tga", img)     # not a format of RendererCore::saveImage
 
 
 def test_headless_example_compiles_against_the_host_mirror(tmp_path):
@@ -215,3 +215,28 @@ def test_headless_example_compiles_against_the_host_mirror(tmp_path):
     assert res.returncode == 0, res.stderr[-3000:]
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 2 and "usage:" in run.stderr
+
+
+@pytest.mark.parametrize("w,h,kind", [(64, 48, "smooth"), (131, 67, "smooth"), (17, 9, "noise"), (1, 1, "noise"), (250, 131, "noise")])
+def test_jpg_writer_decodes_with_independent_decoders(tmp_path, w, h, kind):
+    """saveImage(".jpg") (RendererCore.cpp:175-176: stb quality 100): baseline JFIF, 4:4:4, unit quantiser,
+    image-optimised Huffman tables.  Pillow and OpenCV (two independent libjpeg-class decoders) must both
+    reproduce the pixels to within the rounding of an 8-bit DCT round trip."""
+    PIL_Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(w * 1000 + h)
+    if kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    else:
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([127 + 120 * np.sin(x / 9.0), 127 + 120 * np.cos(y / 7.0), 127 + 100 * np.sin((x + y) / 11.0)], -1).astype(np.uint8)
+    fn = str(tmp_path / "t.jpg")
+    assert host.write_image(fn, ".jpg", np.ascontiguousarray(img))
+    got = np.asarray(PIL_Image.open(fn).convert("RGB"))
+    assert got.shape == img.shape
+    assert np.abs(got.astype(int) - img.astype(int)).max() <= 4
+    try:
+        import cv2
+    except ImportError:
+        return
+    got2 = cv2.cvtColor(cv2.imread(fn), cv2.COLOR_BGR2RGB)
+    assert np.abs(got2.astype(int) - img.astype(int)).max() <= 4

@@ -163,8 +163,9 @@ bool RendererCore::saveImage(std::string fn, std::string ext)                   
     if (vr_read_rgb8(ctx, rgb.data(), /*flip_vertical=*/1) != VR_OK) { reportAbiError("Error!"); return false; }
     if (ext == ".png") return vr::writePNG(fn, framebuffer_size.x, framebuffer_size.y, rgb.data());
     if (ext == ".bmp") return vr::writeBMP(fn, framebuffer_size.x, framebuffer_size.y, rgb.data());
+    if (ext == ".jpg") return vr::writeJPG(fn, framebuffer_size.x, framebuffer_size.y, rgb.data());   // quality 100, RC:176
     if (ext == ".ppm") return vr::writePPM(fn, framebuffer_size.x, framebuffer_size.y, rgb.data());
-    return false;   // ".jpg" needs a DCT encoder the reference gets from stb_image_write
+    return false;
 }
 
 void RendererCore::readVolumeData(std::string fn)                                     // RC:242-447

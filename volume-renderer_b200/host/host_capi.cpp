@@ -105,6 +105,7 @@ VRH_API int vrh_write_image(const char* fn, const char* ext, int w, int h, const
 {
     const std::string e(ext);
     if (e == ".png") return vr::writePNG(fn, w, h, rgb) ? 1 : 0;
+    if (e == ".jpg") return vr::writeJPG(fn, w, h, rgb) ? 1 : 0;
     if (e == ".bmp") return vr::writeBMP(fn, w, h, rgb) ? 1 : 0;
     if (e == ".ppm") return vr::writePPM(fn, w, h, rgb) ? 1 : 0;
     return 0;
