@@ -162,6 +162,12 @@ PYREF_CASES = [
     ("tf_default_knots", [(128, 128), (90, 170)]),
     ("window_min_gt_max", [(32, 32)]),
     ("eye_inside", [(80, 45), (10, 10)]),
+    ("u16_aniso_trilinear", [(128, 72), (60, 100)]),
+    ("mip_trilinear_u16", [(128, 72), (200, 40)]),
+    ("pole_camera", [(80, 45), (30, 70)]),
+    ("c1_trilinear_window_ert", [(128, 128), (180, 90)]),
+    ("u16_full_range", [(64, 64)]),
+    ("iteration_cap_10000", [(24, 24)]),
 ]
 
 
