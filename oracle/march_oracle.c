@@ -83,6 +83,18 @@ static void make_frame_consts(const orc_params* p, frame_consts* fc)
     fc->frange = (float)(p->max_val - p->min_val);
 }
 
+/* test accessor: the frame constants as 17 floats (pmin, pmax, half_len, denom, step_dvr, step_mip, fmin,
+ * fmax, frange) so that the product's host-side evaluation can be compared with this one bit for bit */
+void orc_frame_consts(const orc_params* p, float out[17])
+{
+    frame_consts fc;
+    make_frame_consts(p, &fc);
+    for (int i = 0; i < 3; ++i) {
+        out[i] = fc.pmin[i]; out[3 + i] = fc.pmax[i]; out[6 + i] = fc.half_len[i]; out[9 + i] = fc.denom[i];
+    }
+    out[12] = fc.step_dvr; out[13] = fc.step_mip; out[14] = fc.fmin; out[15] = fc.fmax; out[16] = fc.frange;
+}
+
 /* VR.cs:175-192 */
 static inline void cartesian_to_tex(const orc_params* p, const frame_consts* fc,
                                     const float pos[3], float tc[3])

@@ -67,6 +67,10 @@ typedef struct orc_counters {
 int orc_render(const orc_params* p, const void* voxels, float* rgba,
                uint8_t* touch, orc_counters* counters, int nthreads);
 
+/* The per-frame constants of VolumeRenderer.cs:62-83,109,146,122-124 as evaluated by the oracle:
+ * pmin[3], pmax[3], half_len[3], denom[3], step_dvr, step_mip, fmin, fmax, frange. */
+void orc_frame_consts(const orc_params* p, float out[17]);
+
 /* Number of set bits in a touch bitmap of nvoxels bits. */
 uint64_t orc_popcount(const uint8_t* touch, uint64_t nvoxels);
 

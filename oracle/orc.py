@@ -177,6 +177,13 @@ def render(p: Params, voxels: np.ndarray, *, nthreads: int = 1, touch: bool = Fa
     return out, {"rays": cnt.rays, "rays_hit": cnt.rays_hit, "samples": cnt.samples}, tb
 
 
+def frame_consts(p: Params) -> np.ndarray:
+    """pmin[3], pmax[3], half_len[3], denom[3], step_dvr, step_mip, fmin, fmax, frange (float32)."""
+    out = np.zeros(17, dtype=np.float32)
+    lib().orc_frame_consts(C.byref(p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def popcount(tb: np.ndarray, nvoxels: int) -> int:
     return int(lib().orc_popcount(tb.ctypes.data, int(nvoxels)))
 

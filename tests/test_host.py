@@ -240,3 +240,35 @@ def test_jpg_writer_decodes_with_independent_decoders(tmp_path, w, h, kind):
         return
     got2 = cv2.cvtColor(cv2.imread(fn), cv2.COLOR_BGR2RGB)
     assert np.abs(got2.astype(int) - img.astype(int)).max() <= 4
+
+
+def test_frame_constants_match_the_oracle_bit_for_bit():
+    """The per-frame constants (bounding box :62-83, tex-coord denominators :179, step :109/:146, window
+    floats :122-124) are evaluated on the HOST in the product (csrc/frame.h) and once more in the oracle:
+    every one of them must carry the same bits for arbitrary dims / spacings / view flags / windows /
+    step scales, or no kernel could be bit-exact for that volume."""
+    import volren_b200 as vb
+    rng = np.random.default_rng(2026)
+    cam = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 3, 1, 0, 0, 3, 1, 3.7320508], dtype=np.float32)
+    for it in range(400):
+        if it % 4 == 0:
+            dims = tuple(int(2 ** rng.integers(0, 12)) for _ in range(3))
+            vs = tuple(float(2.0 ** rng.integers(-2, 3)) for _ in range(3))
+        else:
+            dims = tuple(int(x) for x in rng.integers(1, 2049, 3))
+            vs = tuple(float(np.float32(x)) for x in rng.uniform(0.2, 4.0, 3))
+        kw = dict(alpha_scale=float(np.float32(rng.uniform(0, 1))), min_val=int(rng.integers(-50, 3000)),
+                  max_val=int(rng.integers(-50, 70000)), is_mip=int(rng.integers(0, 2)),
+                  view_top=int(rng.integers(0, 2)), view_bottom=int(rng.integers(0, 2)),
+                  step_scale=float(np.float32(rng.choice([1.0, 0.5, 0.25, 2.0, rng.uniform(0.05, 3.0)]))))
+        mine = host.frame_consts(640, 480, dims, vs, cam, vb.default_params(filter=1, **kw))
+        ref = orc.frame_consts(orc.make_params(640, 480, dims, 2, cam, voxel_size=vs, filter=1, **kw))
+        what = f"dims {dims} spacing {vs} {kw}"
+        assert np.array_equal(mine[:12].view(np.uint32), ref[:12].view(np.uint32)), what      # pmin, pmax, half_len, denom
+        step_ref = ref[13] if kw["is_mip"] else ref[12]
+        assert mine[12:13].view(np.uint32)[0] == np.float32(step_ref).view(np.uint32), what
+        assert np.array_equal(mine[13:16].view(np.uint32), ref[14:17].view(np.uint32)), what   # fmin, fmax, frange
+        # derived values the kernels rely on: correctly rounded reciprocals, division mode
+        assert np.array_equal(mine[16:19], (np.float32(1.0) / mine[9:12]).astype(np.float32)), what
+        pow2 = all(float(d) > 0 and np.frexp(float(d))[0] == 0.5 for d in mine[9:12])
+        assert int(mine[20]) == (0 if pow2 else 1), what

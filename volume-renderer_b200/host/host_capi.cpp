@@ -11,6 +11,7 @@
 #include "ImageIO.h"
 #include "RendererCore.h"
 #include "VolumeIO.h"
+#include "../csrc/frame.h"      // host-side evaluation of the per-frame constants (header only)
 
 #define VRH_API extern "C" __attribute__((visibility("default")))
 
@@ -187,3 +188,19 @@ VRH_API void vrh_core_strings(RendererCore* r, char* title, char* msg, char* dat
 }
 VRH_API void vrh_core_clear_popup(RendererCore* r) { r->title.clear(); r->msg.clear(); }   // RendererGUI.cpp:90-96
 VRH_API void vrh_core_histogram(RendererCore* r, float out[256]) { std::memcpy(out, r->histogram.data(), 256 * sizeof(float)); }
+
+// ---- per-frame constants as the product evaluates them on the host (csrc/frame.h), for the CPU tests:
+//      pmin[3], pmax[3], half_len[3], denom[3], step, fmin, fmax, frange, inv_denom[3], inv_frange, tc_div_mode
+VRH_API void vrh_frame_consts(int W, int H, const int32_t dim[3], const float voxel_size[3], const float cam21[21],
+                              const vr_params* p, float out[22])
+{
+    vr::FrameConsts fc;
+    std::memset(&fc, 0, sizeof fc);
+    vr::compute_frame_consts(fc, W, H, dim, voxel_size, cam21, *p);
+    for (int i = 0; i < 3; ++i) {
+        out[i] = fc.pmin[i]; out[3 + i] = fc.pmax[i]; out[6 + i] = fc.half_len[i]; out[9 + i] = fc.denom[i];
+        out[16 + i] = fc.inv_denom[i];
+    }
+    out[12] = fc.step; out[13] = fc.fmin; out[14] = fc.fmax; out[15] = fc.frange;
+    out[19] = fc.inv_frange; out[20] = (float)fc.tc_div_mode; out[21] = (float)fc.win_div_mode;
+}

@@ -277,3 +277,15 @@ class RendererCore:
         out = (C.c_float * 256)()
         hlib().vrh_core_histogram(self._p, C.byref(out))
         return np.array(out[:], dtype=np.float32)
+
+
+def frame_consts(width, height, dims, voxel_size, cam21, params) -> np.ndarray:
+    """The product's host-side per-frame constants (csrc/frame.h): pmin[3], pmax[3], half_len[3], denom[3],
+    step, fmin, fmax, frange, inv_denom[3], inv_frange, tc_div_mode, win_div_mode."""
+    H = hlib()
+    out = np.zeros(22, dtype=np.float32)
+    d = (C.c_int32 * 3)(*[int(x) for x in dims])
+    vs = (C.c_float * 3)(*[float(x) for x in voxel_size])
+    cam = (C.c_float * 21)(*[float(x) for x in cam21])
+    H.vrh_frame_consts(int(width), int(height), d, vs, cam, C.byref(params), out.ctypes.data_as(C.c_void_p))
+    return out
