@@ -11,7 +11,9 @@
  *     length(v) = sqrt(dot(v,v))            clamp(x,a,b) = min(max(x,a),b)
  *     cross(a,b) = (a.y*b.z - b.y*a.z, a.z*b.x - b.z*a.x, a.x*b.y - b.x*a.y)
  *     rotate(I, angle, (0,1,0)) * (1,0,0,0) = (cos, 0, -sin, 0)
- * "parity unpinned" at the glm boundary; known answers are in the tests.
+ * PINNED to the reference source: src/Camera.cpp is compiled unmodified into oracle/_ref/libhost_ref.so
+ * (against the GLM stand-in oracle/shim/glm) and this restatement equals it bit for bit over random walks
+ * (tests/test_reference_pinning.py); "parity unpinned" only at the GLM boundary itself.
  */
 #include "oracle.h"
 

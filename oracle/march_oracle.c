@@ -7,10 +7,13 @@
  *     gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math
  * so that the compiler neither contracts a*b+c into an FMA nor reassociates.
  *
- * "parity unpinned": the reference has no tests / golden images for this path and cannot
- * be executed here (no GL stack).  GLSL leaves the precision of normalize/length/division
- * implementation-defined; the IEEE definitions below are the contract the CUDA path is
- * checked against.
+ * PINNED to the reference source: the shader text itself is compiled for the CPU into
+ * oracle/_ref/libshader_ref.so (oracle/Makefile, oracle/shim/glsl_compat.h) and this restatement
+ * equals it bit for bit (tests/test_reference_pinning.py).  This file stays because it also
+ * carries the extensions the shader does not have (step override, transfer function, opacity
+ * correction), the touch bitmap and the hit counter.  GLSL leaves the precision of
+ * normalize/length/division implementation-defined; the IEEE definitions below (the same as
+ * in glsl_compat.h) are the contract the CUDA path is checked against.
  *
  * Line references "VR.cs:n" are to /root/reference/VolumeRenderer.cs.
  */

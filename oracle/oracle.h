@@ -9,18 +9,23 @@
  * anything declared here.  Only tests/, __graft_entry__.smoke() and the cpu_baseline /
  * --impl reference legs of bench.py use it, and only as the checker.
  *
- * PARITY PINNING
- *   - march / camera / spline: the reference ships no tests, golden images or known-answer
- *     vectors and cannot be executed (no GL stack, no glm) -> "parity unpinned" against a
- *     running reference; pinned only against the hand-derived known answers of SURVEY.md 8(c)
- *     (tests/test_oracle_*.py) and the closed forms of the shader's compositing recurrence.
- *     Third-party arithmetic that is not under /root/reference: glm (un-vendored, no version
- *     pinned anywhere) and the GL driver's GLSL built-ins; each is restated as one correctly
- *     rounded IEEE-754 binary32 operation per GLSL/glm operator, in source order, no FMA
- *     contraction (compile with -ffp-contract=off).
- *   - codec: pinned against the reference's own src/ddsbase.cpp compiled unmodified from
- *     /root/reference into oracle/_ref/ (see oracle/Makefile) and against the golden .pvm
- *     fixtures it wrote (tests/golden/).
+ * PARITY PINNING -- every part is pinned to the reference's OWN SOURCES, compiled where they lie under
+ * /root/reference into oracle/_ref/ (oracle/Makefile; nothing is copied into the repo), and compared bit
+ * for bit by tests/test_reference_pinning.py and tests/test_codec.py:
+ *   - march: VolumeRenderer.cs itself -- the GLSL text, streamed through a 6-line sed (drops #version /
+ *     layout qualifiers / forward declarations, `out T x` -> `T& x`) into g++ as the body of a C++ struct,
+ *     with oracle/shim/glsl_compat.h supplying the GLSL types and built-ins -> _ref/libshader_ref.so.
+ *     march_oracle.c equals it on every scenario that uses reference semantics, on random frames, and on
+ *     the committed fixtures tests/golden/ref_*.npz that shader wrote.  What GLSL leaves implementation-
+ *     defined (precision of normalize/length/division, texture filtering of an integer texture) is defined
+ *     in glsl_compat.h as one correctly rounded IEEE-754 binary32 operation per operator -- a real GL
+ *     driver may differ there in the last ulp; that boundary cannot be pinned without a GL stack.
+ *     The extensions (step override, transfer function, opacity correction) do not exist in the shader and
+ *     are pinned only through their identity settings.
+ *   - camera / spline: src/Camera.cpp and src/CubicSpline.cpp, unmodified -> _ref/libhost_ref.so, built
+ *     against a stand-in for GLM (oracle/shim/glm): GLM is a third-party dependency the reference neither
+ *     vendors nor pins; the stand-in restates GLM 0.9.8/0.9.9's published generic definitions.
+ *   - codec: src/ddsbase.cpp, unmodified -> _ref/libddsbase_ref.so, plus the golden .pvm fixtures it wrote.
  */
 #ifndef VOLREN_ORACLE_H
 #define VOLREN_ORACLE_H

@@ -1,4 +1,6 @@
-"""ctypes bindings for oracle/liboracle.so and oracle/_ref/libddsbase_ref.so.
+"""ctypes bindings for oracle/liboracle.so and the reference's own sources compiled into oracle/_ref/
+(libddsbase_ref.so = src/ddsbase.cpp, libhost_ref.so = src/Camera.cpp + src/CubicSpline.cpp,
+libshader_ref.so = VolumeRenderer.cs compiled as C++ through oracle/shim/glsl_compat.h).
 
 TEST INFRASTRUCTURE ONLY (see oracle/oracle.h): the checker, never the product.
 """
@@ -13,6 +15,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_LIB_PATH = os.path.join(HERE, "_ref", "libddsbase_ref.so")
+REF_HOST_LIB_PATH = os.path.join(HERE, "_ref", "libhost_ref.so")
+REF_SHADER_LIB_PATH = os.path.join(HERE, "_ref", "libshader_ref.so")
 
 FILTER_NEAREST = 0
 FILTER_TRILINEAR = 1
@@ -21,9 +25,13 @@ FILTER_TRILINEAR = 1
 def build(force: bool = False) -> None:
     """Compile the oracle (and, when /root/reference is present, oracle/_ref)."""
     srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h", ".cpp"))]
+    shim = os.path.join(HERE, "shim")
+    for root, _, files in os.walk(shim):
+        srcs += [os.path.join(root, f) for f in files]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    need_ref = os.path.exists("/root/reference/src/ddsbase.cpp") and not os.path.exists(REF_LIB_PATH)
+    need_ref = os.path.exists("/root/reference/src/ddsbase.cpp") and not all(
+        os.path.exists(q) for q in (REF_LIB_PATH, REF_HOST_LIB_PATH, REF_SHADER_LIB_PATH))
     if stale or need_ref:
         subprocess.run(["make", "-C", HERE, "-s"] + (["-B"] if force else []), check=True)
 
@@ -132,6 +140,48 @@ def ref_lib():
     return _ref
 
 
+_ref_shader = None
+_ref_host = None
+
+
+def ref_shader_lib():
+    """The reference's own VolumeRenderer.cs compiled for the CPU (oracle/_ref); None when never built."""
+    global _ref_shader
+    if _ref_shader is None:
+        build()
+        if not os.path.exists(REF_SHADER_LIB_PATH):
+            return None
+        S = C.CDLL(REF_SHADER_LIB_PATH)
+        S.shader_ref_render.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
+        S.shader_ref_render.restype = C.c_int
+        _ref_shader = S
+    return _ref_shader
+
+
+def ref_host_lib():
+    """The reference's own Camera.cpp + CubicSpline.cpp (oracle/_ref); None when never built."""
+    global _ref_host
+    if _ref_host is None:
+        build()
+        if not os.path.exists(REF_HOST_LIB_PATH):
+            return None
+        Hh = C.CDLL(REF_HOST_LIB_PATH)
+        Hh.ref_camera_new.argtypes = [C.c_float, C.c_float, C.c_float]
+        Hh.ref_camera_new.restype = C.c_void_p
+        Hh.ref_camera_delete.argtypes = [C.c_void_p]
+        Hh.ref_camera_reset.argtypes = [C.c_void_p]
+        Hh.ref_camera_set_orientation.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+        Hh.ref_camera_state.argtypes = [C.c_void_p, C.POINTER(C.c_float * 37), C.POINTER(C.c_int * 2)]
+        Hh.ref_camera_state.restype = C.c_int
+        Hh.ref_spline_new.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        Hh.ref_spline_new.restype = C.c_void_p
+        Hh.ref_spline_delete.argtypes = [C.c_void_p]
+        Hh.ref_spline_eval_iso.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float * 4)]
+        Hh.ref_spline_eval_t.argtypes = [C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_float * 4)]
+        _ref_host = Hh
+    return _ref_host
+
+
 # --------------------------------------------------------------------------- march
 
 def make_params(width, height, dim, bytes_per_voxel, cam21, *, voxel_size=(1.0, 1.0, 1.0),
@@ -177,6 +227,27 @@ def render(p: Params, voxels: np.ndarray, *, nthreads: int = 1, touch: bool = Fa
     return out, {"rays": cnt.rays, "rays_hit": cnt.rays_hit, "samples": cnt.samples}, tb
 
 
+def ref_render(p: Params, voxels: np.ndarray, *, nthreads: int = 1, out: np.ndarray = None):
+    """The REFERENCE's own shader (VolumeRenderer.cs compiled for the CPU, oracle/_ref/libshader_ref.so) on
+    the same parameter block.  Only reference semantics: raises for step_scale != 1, TF, opacity correction.
+    Returns (rgba[H,W,4], counters dict with rays / samples) or None when oracle/_ref was never built."""
+    S = ref_shader_lib()
+    if S is None:
+        return None
+    vox = np.ascontiguousarray(voxels)
+    assert vox.dtype == (np.uint8 if p.bytes_per_voxel == 1 else np.uint16)
+    assert vox.size == p.dim[0] * p.dim[1] * p.dim[2]
+    if out is None:
+        out = np.zeros((p.height, p.width, 4), dtype=np.float32)
+    cnt = Counters()
+    rc = S.shader_ref_render(C.byref(p), vox.ctypes.data, out.ctypes.data, C.byref(cnt), int(nthreads))
+    if rc == -2:
+        raise ValueError("the reference shader has no step override / transfer function / opacity correction")
+    if rc != 0:
+        raise ValueError("shader_ref_render: bad arguments")
+    return out, {"rays": cnt.rays, "samples": cnt.samples}
+
+
 def frame_consts(p: Params) -> np.ndarray:
     """pmin[3], pmax[3], half_len[3], denom[3], step_dvr, step_mip, fmin, fmax, frange (float32)."""
     out = np.zeros(17, dtype=np.float32)
@@ -204,6 +275,64 @@ class OracleCamera:
     def ubo(self) -> np.ndarray:
         out = (C.c_float * 21)()
         lib().orc_camera_ubo(C.byref(self.c), C.byref(out))
+        return np.array(out[:], dtype=np.float32)
+
+
+class RefCamera:
+    """The reference's own Camera class (src/Camera.cpp compiled into oracle/_ref/libhost_ref.so)."""
+
+    def __init__(self, y_fov=30.0, rot_speed=0.7, mov_speed=0.3):
+        self.h = ref_host_lib().ref_camera_new(y_fov, rot_speed, mov_speed)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref_host_lib().ref_camera_delete(self.h)
+            self.h = None
+
+    def reset(self):
+        ref_host_lib().ref_camera_reset(self.h)
+
+    def set_orientation(self, zoom, zenith, azimuth):
+        ref_host_lib().ref_camera_set_orientation(self.h, zoom, zenith, azimuth)
+
+    def state(self):
+        """-> (ubo[21], eye[4], side[4], up[4], look_at[4], is_changed before setUBO, after setUBO)"""
+        out = (C.c_float * 37)()
+        ch = (C.c_int * 2)()
+        if ref_host_lib().ref_camera_state(self.h, C.byref(out), C.byref(ch)) != 0:
+            raise RuntimeError("Camera::setUBO did not emit 21 floats")
+        a = np.array(out[:], dtype=np.float32)
+        return a[:21], a[21:25], a[25:29], a[29:33], a[33:37], bool(ch[0]), bool(ch[1])
+
+    def ubo(self) -> np.ndarray:
+        return self.state()[0]
+
+
+class RefSpline:
+    """The reference's own CubicSpline class (src/CubicSpline.cpp compiled into oracle/_ref/libhost_ref.so)."""
+
+    def __init__(self, knots):
+        n = len(knots)
+        iso = (C.c_int * n)(*[int(k[0]) for k in knots])
+        col = (C.c_float * (4 * n))()
+        for i, k in enumerate(knots):
+            c4 = k[1] if isinstance(k[1], (tuple, list)) else (0.0, 0.0, 0.0, k[1])
+            col[i * 4:(i + 1) * 4] = [float(v) for v in c4]
+        self.h = ref_host_lib().ref_spline_new(n, iso, col)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref_host_lib().ref_spline_delete(self.h)
+            self.h = None
+
+    def eval_iso(self, iso) -> np.ndarray:
+        out = (C.c_float * 4)()
+        ref_host_lib().ref_spline_eval_iso(self.h, int(iso), C.byref(out))
+        return np.array(out[:], dtype=np.float32)
+
+    def eval_t(self, t, seg) -> np.ndarray:
+        out = (C.c_float * 4)()
+        ref_host_lib().ref_spline_eval_t(self.h, float(t), int(seg), C.byref(out))
         return np.array(out[:], dtype=np.float32)
 
 

@@ -4,6 +4,8 @@
  * Restatement of /root/reference/src/CubicSpline.cpp ("CS:n"): natural cubic spline through
  * N+1 control points in vec4, one rounded fp32 operation per glm operator, source order.
  * Default knots used by the tests: AlphaControlSplineWidget.cpp:56-59.
+ * PINNED to the reference source: src/CubicSpline.cpp compiled unmodified into oracle/_ref/libhost_ref.so
+ * (tests/test_reference_pinning.py compares every iso value of random knot sets bit for bit).
  */
 #include "oracle.h"
 

@@ -32,6 +32,8 @@ def volume(name):
         return np.full(16 * 16 * 16, 100, dtype=np.uint8), (16, 16, 16), 1, (1.0, 1.0, 1.0)
     if name == "one_voxel_u8":
         return np.array([200], dtype=np.uint8), (1, 1, 1), 1, (1.0, 1.0, 1.0)
+    if name == "rod_1x1x12000_u8":  # |vol_size| = 12000 > 10000 samples along z at the REFERENCE step (no step override)
+        return np.full(12000, 3, dtype=np.uint8), (1, 1, 12000), 1, (2000.0, 2000.0, 1.0)
     raise KeyError(name)
 
 
@@ -87,12 +89,20 @@ CASES = [
     ("one_voxel", "one_voxel_u8", "K0", (64, 64), dict(alpha_scale=0.7, min_val=0, max_val=255, filter=1)),
     # VolumeRenderer.cs:115: the loop stops after 10000 samples (16 voxels / (step 1/16 * 0.001) = 16000 > 10000)
     ("iteration_cap_10000", "const_u8", "K0", (48, 48), dict(alpha_scale=0.00001, min_val=0, max_val=255, filter=1, step_scale=0.001)),
+    # the same cap reached WITHOUT the step override (so the reference's own shader can run it): a 1x1x12000 rod seen end-on
+    ("iteration_cap_reference", "rod_1x1x12000_u8", "K0", (40, 40), dict(alpha_scale=0.001, min_val=0, max_val=255, filter=0)),
     ("half_step_opacity_corrected", "smooth64_u8", "K1", (128, 128), dict(alpha_scale=0.1, min_val=0, max_val=255, filter=1, step_scale=0.5, opacity_correction=1)),
 ]
 
 # cases whose result may legitimately differ from the oracle in the last bits (double pow on
 # the GPU vs glibc); they are held to TOL only
 TOLERANCE_ONLY = {"half_step_opacity_corrected"}
+
+
+def is_reference_semantics(kw):
+    """True when the case uses nothing VolumeRenderer.cs does not have (step override, TF, opacity correction):
+    such a case can be run through the reference's own shader (oracle/_ref/libshader_ref.so)."""
+    return kw.get("step_scale", 1.0) == 1.0 and not kw.get("tf", False) and not kw.get("opacity_correction", 0)
 
 
 def case_by_id(cid):
