@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--camera", default="K2", choices=["K0", "K1", "K2"])
     ap.add_argument("--alpha", type=float, default=0.02)
     ap.add_argument("--filter", default="trilinear", choices=["nearest", "trilinear"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "windowed", "fast", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu", "nearest_tex"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "texpair_pipe", "nearest_tex"])
     ap.add_argument("--cpu-row-stride", type=int, default=1, help="cpu_baseline renders every n-th row")
     ap.add_argument("--mip", action="store_true", help="maximum-intensity projection (the reference's use_mip toggle)")
     ap.add_argument("--tf", action="store_true", help="CubicSpline transfer function (default alpha knots of the reference's TF editor)")
@@ -228,8 +228,7 @@ def run_ours(args):
     W, H = cfg["image"]
     dims, bpv = cfg["dims"], cfg["bpv"]
     cam = workloads.camera_block(args.camera)
-    kernel = {"auto": vb.KERNEL_AUTO, "direct": vb.KERNEL_DIRECT, "windowed": vb.KERNEL_WINDOWED, "fast": vb.KERNEL_FAST, "texgather": vb.KERNEL_TEXGATHER,
-              "texpair": vb.KERNEL_TEXPAIR, "texpair2": vb.KERNEL_TEXPAIR2, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "hybrid": vb.KERNEL_HYBRID, "zlsu": vb.KERNEL_ZLSU, "nearest_tex": vb.KERNEL_NEAREST_TEX}[args.kernel]
+    kernel = {"auto": vb.KERNEL_AUTO, "direct": vb.KERNEL_DIRECT, "texpair_pipe": vb.KERNEL_TEXPAIR_PIPE, "nearest_tex": vb.KERNEL_NEAREST_TEX}[args.kernel]
     params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
                                filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
                                step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None,

@@ -40,29 +40,30 @@ typedef enum vr_status {
     VR_ERR_NO_VOLUME = -3,      /* render before upload                           */
     VR_ERR_OOM = -4,
     VR_ERR_IO = -5,
-    VR_ERR_FORMAT = -6          /* malformed .raw.inf / .pvm                      */
+    VR_ERR_FORMAT = -6,         /* malformed .raw.inf / .pvm                      */
+    VR_ERR_TIMEOUT = -7         /* a peer-frame barrier wait gave up              */
 } vr_status;
 
 enum { VR_FILTER_NEAREST = 0, VR_FILTER_TRILINEAR = 1 };
 
 /* kernel selection (all produce bit-identical images):
- *   DIRECT   one thread per ray, texels straight from HBM through L1/L2; handles every mode
- *   FAST     same data path, issue-slot-optimised loop (DVR, default view, no TF)
- *   WINDOWED persistent screen-tile CTAs marching through TMA-staged shared-memory windows
- *   TEXGATHER trilinear only: the 2x2 texel footprint of each slice fetched with one exact
- *            texture-gather (tld4) from a layered CUDA array; interpolation stays in fp32 ALU
- *   TEXPAIR  trilinear only: layered array of (z, z+1) voxel pairs, so ONE tld4 returns all eight
- *            texels of a sample; one or two rays per thread (TEXPAIR2: cross-ray f32x2 packing);
- *            TEXPAIR_PIPE: software-pipelined, two gathers in flight per warp;
- *            HYBRID: same pipeline, even samples through the texture unit, odd samples through the
- *            LSU (ld.global.nc of the same z-pair words from a linear copy); ZLSU: LSU only
- *   NEAREST_TEX nearest filter only: one integer-coordinate texel load (TLD) per sample from the
- *            source-type layered array, software pipelined
- *   AUTO     the fastest kernel that covers the frame's parameters
- * A request the frame's parameters do not allow falls back (TEXPAIR -> TEXGATHER/WINDOWED -> FAST -> DIRECT). */
-enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_WINDOWED = 2, VR_KERNEL_FAST = 3, VR_KERNEL_TEXGATHER = 4,
-       VR_KERNEL_TEXPAIR = 5, VR_KERNEL_TEXPAIR2 = 6, VR_KERNEL_TEXPAIR_PIPE = 7,
-       VR_KERNEL_HYBRID = 8, VR_KERNEL_ZLSU = 9, VR_KERNEL_NEAREST_TEX = 10 };
+ *   DIRECT       one thread per ray, texels straight from the edge-replicated linear copy through L1/L2;
+ *                handles every parameter combination, including the degenerate ones (min_val >= max_val,
+ *                negative alpha_scale, non-finite LUT entries); also the instrumentation pass
+ *   TEXPAIR_PIPE trilinear filter: layered array of (z, z+1) voxel pairs, ONE texture gather (tld4) returns the
+ *                eight texels of a sample; software pipelined; forms for DVR / TF / MIP / view swizzles /
+ *                opacity correction; optional result-identical empty-space skipping
+ *   NEAREST_TEX  nearest filter (the reference's de-facto output): one integer-coordinate texel load (TLD) per
+ *                sample from the source-type layered array; same pipeline, forms and skipping
+ *   AUTO         TEXPAIR_PIPE or NEAREST_TEX by filter; DIRECT for frames they do not cover
+ * A request the frame's parameters do not allow falls back to DIRECT.  (Values 2-6, 8, 9 were development
+ * kernels of round 1 -- windowed TMA, LSU, two-gather, hybrids -- measured slower; they live in tools/lab.) */
+enum { VR_KERNEL_AUTO = 0, VR_KERNEL_DIRECT = 1, VR_KERNEL_TEXPAIR_PIPE = 7, VR_KERNEL_NEAREST_TEX = 10 };
+
+/* empty-space skipping (result-identical; see vr_cell_table_get) */
+enum { VR_SKIP_AUTO = 0,   /* used when it pays: enough cells are empty under the current window */
+       VR_SKIP_ON = 1,     /* whenever it is valid */
+       VR_SKIP_OFF = 2 };
 
 typedef struct vr_context vr_context;
 
@@ -83,6 +84,7 @@ typedef struct vr_params {
     int32_t use_tf;             /* src.a = tf_lut[round(v*255)] instead of src.a = v           */
     float   tf_lut[256];
     int32_t kernel;             /* VR_KERNEL_*                                                 */
+    int32_t empty_skip;         /* VR_SKIP_*                                                   */
 } vr_params;
 
 typedef struct vr_render_stats {
@@ -91,7 +93,18 @@ typedef struct vr_render_stats {
     float    total_ms;          /* whole call incl. copies (host-side clock)                   */
     uint32_t kernel_launches;   /* kernels of this library launched by the call                */
     uint32_t kernel_used;       /* VR_KERNEL_* actually run                                    */
+    uint32_t skip_used;         /* 1: the empty-space skipping form of that kernel ran         */
 } vr_render_stats;
+
+/* footprint of the volume in this GPU's HBM, bytes (0 = that copy does not exist; the arrays are built on the
+ * first frame that needs them) */
+typedef struct vr_memory_info {
+    uint64_t linear_bytes;          /* edge-replicated linear copy (DIRECT kernel, source of the others)  */
+    uint64_t array_bytes;           /* source-type layered array (NEAREST_TEX)                            */
+    uint64_t zpair_array_bytes;     /* z-pair layered array (TEXPAIR_PIPE): 2x the volume                 */
+    uint64_t cell_table_bytes;      /* per-cell min/max + empty map                                       */
+    uint64_t frame_bytes;
+} vr_memory_info;
 
 typedef struct vr_volume_stats {
     int32_t min_value, max_value;   /* RendererCore.cpp:362-384                                */
@@ -126,6 +139,16 @@ VR_API int vr_set_voxel_size(vr_context* ctx, const float voxel_size[3]);
 /* ---- min/max scan + 256-bin histogram on the GPU: RendererCore.cpp:360-405
  *      (64-bit safe; the reference's skip of index 8390640 is not replicated) ---- */
 VR_API int vr_volume_stats_get(vr_context* ctx, vr_volume_stats* out);
+
+/* ---- per-cell min/max table built at upload (the brick table of SURVEY.md 8f-2; no reference counterpart --
+ *      the reference marches every sample, VolumeRenderer.cs:115-137).  Cells are cubes of 2^shift voxels;
+ *      cell c covers, per axis, voxel indices [c*2^shift - 1, (c+1)*2^shift - 1] clamped to the volume (every
+ *      voxel a sample based in the cell can touch); cells[a] = (dims[a] >> shift) + 1.  mins / maxs may be NULL;
+ *      otherwise they receive cells[0]*cells[1]*cells[2] values, x fastest.  `empty_cells` = cells whose max
+ *      is <= the current min_val, i.e. whose samples contribute exactly 0 (skipped by the SKIP kernels). ---- */
+VR_API int vr_cell_table_get(vr_context* ctx, int* shift, int cells[3], uint16_t* mins, uint16_t* maxs,
+                             uint64_t* empty_cells);
+VR_API int vr_memory_info_get(vr_context* ctx, vr_memory_info* out);
 
 /* ---- camera block: replaces glBufferData(GL_UNIFORM_BUFFER, 84 bytes) RendererCore.cpp:
  *      221-240; the same 21 floats Camera::setUBO emits (Camera.cpp:59-80): mat4 view_mat
@@ -191,6 +214,14 @@ VR_API int vr_peer_frame_release(vr_context* ctx, float* d_target_frame, uint32_
                                  void* cuda_stream);
 VR_API int vr_peer_frame_status(vr_context* ctx, float* d_target_frame, uint32_t* arrivals,
                                 uint32_t* released, uint32_t* timed_out);
+/* render + arrive in one call: this rank's row tiles are stored straight into `d_target_frame` (own or peer
+ * frame) and the LAST CTA of the march kernel to finish publishes the arrival in the owner's barrier word, so no
+ * separate signal kernel runs; on the owner the bounded wait for all `world` arrivals follows on the stream.
+ * A wait that timed out in an earlier frame makes this call (and arrive / release) fail with VR_ERR_TIMEOUT until
+ * vr_peer_frame_reset is called: a torn frame is never consumed silently. */
+VR_API int vr_render_peer(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int world, int is_owner,
+                          void* cuda_stream, vr_render_stats* stats);
+VR_API int vr_peer_frame_reset(vr_context* ctx, float* d_target_frame);
 
 /* ---- display/save step after the path: float RGBA -> RGB8 (clamp, no gamma), vertical
  *      flip; replaces glBlitFramebuffer/glReadPixels, RendererCore.cpp:158-171 ---- */

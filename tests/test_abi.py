@@ -38,13 +38,14 @@ def test_params_default_matches_reference_constructor():
     assert p.alpha_scale == 1.0 and p.min_val == 0 and p.max_val == 0
     assert p.is_mip == 0 and p.view_top == 0 and p.view_bottom == 0
     assert p.filter == vb.FILTER_NEAREST and p.step_scale == 1.0 and p.use_tf == 0
-    assert p.opacity_correction == 0 and p.kernel == vb.KERNEL_AUTO
+    assert p.opacity_correction == 0 and p.kernel == vb.KERNEL_AUTO and p.empty_skip == vb.SKIP_AUTO
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(vb.Params) == 4 * 10 + 256 * 4 + 4
-    assert C.sizeof(vb.RenderStats) == 16
+    assert C.sizeof(vb.Params) == 4 * 10 + 256 * 4 + 4 + 4
+    assert C.sizeof(vb.RenderStats) == 20
     assert C.sizeof(vb.VolumeStats) == 8 + 1024
+    assert C.sizeof(vb.MemoryInfo) == 40
 
 
 def test_no_cpu_fallback_without_gpu():

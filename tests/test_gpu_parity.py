@@ -1,7 +1,11 @@
-"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle -- and, where the reference's own shader
+compiled for the CPU is present (oracle/_ref/libshader_ref.so travels with the snapshot), directly against
+the reference -- on the same seeded inputs.
 
 Bar: north_star tolerance 1e-4 per channel (util.TOL) -- and, because the device code issues
 the same correctly-rounded operation sequence as the oracle, exact bit equality."""
+import os
+
 import numpy as np
 import pytest
 
@@ -13,42 +17,69 @@ from util import TOL, compare, oracle_frame
 
 pytestmark = pytest.mark.gpu
 
+OPTIMISED = (vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_NEAREST_TEX)
 
-def run_product(vox, dims, voxel_size, cam, W, H, vkw, kernel=vb.KERNEL_AUTO, partition=None):
+
+def run_product(vox, dims, voxel_size, cam, W, H, vkw, kernel=vb.KERNEL_AUTO, partition=None, skip=vb.SKIP_AUTO):
     with vb.Context(W, H) as ctx:
         ctx.upload_volume(vox, dims, voxel_size)
         ctx.set_camera(cam)
-        ctx.set_params(vb.default_params(kernel=kernel, **vkw))
+        ctx.set_params(vb.default_params(kernel=kernel, empty_skip=skip, **vkw))
         if partition:
             ctx.set_partition(*partition)
         img, st = ctx.render()
         return img, st
 
 
+def expected_kernel(kw):
+    return vb.KERNEL_TEXPAIR_PIPE if kw.get("filter", 0) == 1 else vb.KERNEL_NEAREST_TEX
+
+
+# scenarios the optimised kernels do not cover by design: they must take the generic loop
+DEGENERATE = {"window_min_eq_max_nan", "window_min_gt_max"}
+# volumes deeper than a layered CUDA array (2048 layers)
+TOO_DEEP = {"iteration_cap_reference"}
+
+
 @pytest.mark.parametrize("cid", [c[0] for c in scenarios.CASES])
-@pytest.mark.parametrize("kernel", [vb.KERNEL_DIRECT, vb.KERNEL_AUTO, vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER,
-                                    vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU,
-                                    vb.KERNEL_NEAREST_TEX],
-                         ids=["direct", "auto", "fast", "windowed", "texgather", "texpair", "texpair2", "texpair_pipe", "hybrid", "zlsu",
-                              "nearest_tex"])
-def test_case_matches_oracle(cid, kernel):
+@pytest.mark.parametrize("mode", ["direct", "auto", "auto_skip"])
+def test_case_matches_oracle(cid, mode):
     _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
     vox, dims, bpv, vs = scenarios.volume(vname)
     cam = scenarios.camera(cname)
     okw, vkw = scenarios.split_kwargs(kw)
     ref, cnt = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
-    img, st = run_product(vox, dims, vs, cam, W, H, vkw, kernel=kernel)
+    kernel = vb.KERNEL_DIRECT if mode == "direct" else vb.KERNEL_AUTO
+    skip = vb.SKIP_ON if mode == "auto_skip" else vb.SKIP_OFF
+    img, st = run_product(vox, dims, vs, cam, W, H, vkw, kernel=kernel, skip=skip)
     assert st.kernel_launches >= 1 and st.kernel_ms > 0
+    if mode == "direct" or cid in DEGENERATE or cid in TOO_DEEP:
+        assert st.kernel_used == vb.KERNEL_DIRECT
+    else:
+        assert st.kernel_used == expected_kernel(kw), f"{cid}: fell back to kernel {st.kernel_used}"
+    # tolerance-only: per-sample opacity correction evaluates a double-precision pow (CUDA vs glibc)
     compare(img, ref, cid, exact=cid not in scenarios.TOLERANCE_ONLY)
     if cid not in ("window_min_eq_max_nan",):
         assert cnt["rays_hit"] > 0 and np.isfinite(img).all()
+
+
+@pytest.mark.skipif(orc.ref_shader_lib() is None, reason="oracle/_ref/libshader_ref.so not built")
+@pytest.mark.parametrize("cid", [c[0] for c in scenarios.CASES if scenarios.is_reference_semantics(c[4])])
+def test_case_matches_the_reference_shader_itself(cid):
+    """No restatement in between: the CUDA frame against VolumeRenderer.cs compiled for the CPU."""
+    _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    cam = scenarios.camera(cname)
+    okw, vkw = scenarios.split_kwargs(kw)
+    ref, _ = orc.ref_render(orc.make_params(W, H, dims, bpv, cam, voxel_size=vs, **okw), vox, nthreads=8)
+    img, _ = run_product(vox, dims, vs, cam, W, H, vkw)
+    compare(img, ref, "reference shader " + cid)
 
 
 @pytest.mark.parametrize("cid", ["c1_trilinear_128steps", "ragged_nearest", "u16_aniso_trilinear", "mip_nearest"])
 def test_golden_fixture(cid, golden_dir):
     """Committed fixtures (tests/golden/make_golden.py): inputs are regenerated from the seed,
     the expected image comes from the file, not from running the oracle now."""
-    import os
     g = np.load(os.path.join(golden_dir, f"{cid}.npz"))
     _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
     vox, dims, bpv, vs = scenarios.volume(vname)
@@ -59,27 +90,197 @@ def test_golden_fixture(cid, golden_dir):
     compare(img, g["rgba"], "golden " + cid)
 
 
-@pytest.mark.parametrize("vname,cname,kw", [
-    ("mix64_u8", "K0", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)),
-    ("mix64_u8", "K2", dict(alpha_scale=0.3, min_val=20, max_val=220, filter=1)),
-    ("mix_64x64x32_u16", "K1", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1)),
-    ("rand_40x56x33_u16", "K2", dict(alpha_scale=0.03, min_val=100, max_val=4000, filter=1)),
-])
-def test_optimised_kernels_really_run_and_match(vname, cname, kw):
-    """The FAST and WINDOWED kernels are the ones selected (no silent fallback to DIRECT) for
-    frames they cover, and both reproduce the oracle bit for bit."""
+@pytest.mark.parametrize("cid", ["c1_nearest_ref_step", "ragged_trilinear", "u16_aniso_trilinear", "mip_nearest", "view_top",
+                                 "window_min_gt_max", "iteration_cap_reference"])
+def test_golden_fixture_written_by_the_reference_shader(cid, golden_dir):
+    """tests/golden/ref_*.npz (tests/golden/make_ref_golden.py): images the reference's own shader produced."""
+    g = np.load(os.path.join(golden_dir, f"ref_{cid}.npz"))
+    _, vname, cname, (W, H), kw = scenarios.case_by_id(cid)
+    vox, dims, bpv, vs = scenarios.volume(vname)
+    _, vkw = scenarios.split_kwargs(kw)
+    for skip in (vb.SKIP_OFF, vb.SKIP_ON):
+        img, _ = run_product(vox, dims, vs, g["cam"], W, H, vkw, skip=skip)
+        compare(img, g["rgba"], "reference golden " + cid)
+
+
+# ---------------------------------------------------------------- every mode combination runs in the optimised kernels
+
+COMBOS = [
+    # nearest filter (the reference's de-facto filter) with the GUI's toggles
+    ("mix64_u8", "K1", dict(alpha_scale=0.9, min_val=0, max_val=255, filter=0, is_mip=1)),
+    ("mix64_u8", "K1", dict(alpha_scale=0.3, min_val=0, max_val=255, filter=0, tf=True)),
+    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=0, view_bottom=1)),
+    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=0, max_val=255, filter=0, view_top=1)),
+    ("mix64_u8", "K0", dict(alpha_scale=0.9, min_val=0, max_val=255, filter=0, tf=True, is_mip=1)),
+    ("mix_64x64x32_u16", "K2", dict(alpha_scale=0.7, min_val=1000, max_val=3000, filter=0, is_mip=1, view_top=1)),
+    # trilinear: TF / MIP / views alone and combined
+    ("mix64_u8", "K1", dict(alpha_scale=0.3, min_val=0, max_val=255, filter=1, tf=True)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.08, min_val=30, max_val=200, filter=1, tf=True, step_scale=0.5)),
+    ("mix_64x64x32_u16", "K1", dict(alpha_scale=0.2, min_val=100, max_val=3900, filter=1, tf=True)),
+    ("mix_64x64x32_u16", "K2", dict(alpha_scale=1.0, min_val=1000, max_val=3000, filter=1, is_mip=1)),
+    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.9, min_val=0, max_val=4095, filter=1, is_mip=1, step_scale=0.5)),
+    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=0, max_val=255, filter=1, view_top=1)),
+    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1, view_bottom=1)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1, view_top=1, view_bottom=1)),   # top wins (:186)
+    ("mix64_u8", "K1", dict(alpha_scale=0.8, min_val=0, max_val=255, filter=1, tf=True, is_mip=1)),
+    ("mix64_u8", "K1", dict(alpha_scale=0.3, min_val=10, max_val=240, filter=1, tf=True, view_top=1)),
+    ("mix_64x64x32_u16", "K0", dict(alpha_scale=0.9, min_val=1000, max_val=3000, filter=1, is_mip=1, view_bottom=1)),
+    # opacity correction with a transfer function: final opacity LUT baked on the host -> exact
+    ("smooth64_u8", "K1", dict(alpha_scale=0.4, min_val=0, max_val=255, filter=1, tf=True, step_scale=0.5, opacity_correction=1)),
+    ("mix64_u8", "K2", dict(alpha_scale=0.4, min_val=0, max_val=255, filter=0, tf=True, step_scale=2.0, opacity_correction=1)),
+]
+
+
+@pytest.mark.parametrize("vname,cname,kw", COMBOS)
+def test_mode_combinations_run_in_the_optimised_kernels(vname, cname, kw):
+    """VolumeRenderer.cs:141-173 (MIP), :183-190 (view swizzles), the TF extension and their combinations run in
+    the optimised kernels -- no silent fall-back to the generic loop -- and equal the oracle and the generic
+    DIRECT loop bit for bit."""
     vox, dims, bpv, vs = scenarios.volume(vname)
     cam = scenarios.camera(cname)
     W, H = 320, 200
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
-    for kernel in (vb.KERNEL_FAST, vb.KERNEL_WINDOWED, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU, vb.KERNEL_AUTO):
-        img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
-        if kernel != vb.KERNEL_AUTO:
-            assert st.kernel_used == kernel, f"requested kernel {kernel}, ran {st.kernel_used}"
-        else:
-            assert st.kernel_used in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID)
-        compare(img, ref, f"{vname}/{cname}/kernel{kernel}")
+    okw, vkw = scenarios.split_kwargs(kw)
+    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
+    for skip in (vb.SKIP_OFF, vb.SKIP_ON):
+        img, st = run_product(vox, dims, vs, cam, W, H, vkw, skip=skip)
+        assert st.kernel_used == expected_kernel(kw)
+        compare(img, ref, f"{vname}/{cname}/{kw}")
+    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
+    assert st2.kernel_used == vb.KERNEL_DIRECT
+    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
 
+
+@pytest.mark.parametrize("filt", [0, 1])
+def test_per_sample_opacity_correction_stays_in_the_optimised_kernel(filt):
+    """a' = 1-(1-a)^step_scale without a transfer function: evaluated per sample in double precision inside the
+    optimised kernel (CUDA pow vs glibc pow: held to the north-star tolerance, not to bit equality)."""
+    vox, dims, bpv, vs = scenarios.volume("smooth64_u8")
+    cam = scenarios.camera("K1")
+    kw = dict(alpha_scale=0.1, min_val=0, max_val=255, filter=filt, step_scale=0.5, opacity_correction=1)
+    ref, _ = oracle_frame(cam, vox, dims, bpv, 200, 150, voxel_size=vs, **kw)
+    img, st = run_product(vox, dims, vs, cam, 200, 150, kw)
+    assert st.kernel_used == expected_kernel(kw)
+    compare(img, ref, "opacity correction", exact=False)
+    # alpha_scale > 1 can push (1 - a) below zero: NaN semantics belong to the generic loop
+    kw["alpha_scale"] = 1.5
+    ref, _ = oracle_frame(cam, vox, dims, bpv, 200, 150, voxel_size=vs, **kw)
+    img, st = run_product(vox, dims, vs, cam, 200, 150, kw)
+    assert st.kernel_used == vb.KERNEL_DIRECT
+    both_nan = np.isnan(img) & np.isnan(ref)
+    assert np.allclose(np.where(both_nan, 0, img), np.where(both_nan, 0, ref), atol=TOL, equal_nan=True)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(alpha_scale=-0.5, min_val=0, max_val=255, filter=1, is_mip=1),                 # ADVICE r1: MIP must not render as DVR
+    dict(alpha_scale=-0.5, min_val=0, max_val=255, filter=1, view_top=1),
+    dict(alpha_scale=-0.25, min_val=0, max_val=255, filter=0, tf=True),
+    dict(alpha_scale=0.5, min_val=200, max_val=100, filter=1, is_mip=1),                # unordered window + MIP
+    dict(alpha_scale=0.5, min_val=100, max_val=100, filter=0, view_bottom=1),           # 0/0 window + view
+])
+def test_frames_outside_the_fast_path_keep_their_mode(kw):
+    """Negative alpha_scale / degenerate windows are not covered by the optimised kernels; the generic loop that
+    takes over must still honour MIP, the transfer function and the view swizzles."""
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    okw, vkw = scenarios.split_kwargs(kw)
+    ref, _ = oracle_frame(cam, vox, dims, bpv, 160, 120, voxel_size=vs, **okw)
+    img, st = run_product(vox, dims, vs, cam, 160, 120, vkw)
+    assert st.kernel_used == vb.KERNEL_DIRECT
+    compare(img, ref, str(kw))
+
+
+# ---------------------------------------------------------------- empty-space skipping + the cell table
+
+def shells_volume(n=96, bpv=2):
+    """CT-like: two bright shells in 'air' (values below the window), ~75 % of the voxels empty under [1000, 3000]."""
+    from volren_b200 import workloads
+    vox = workloads.mix_volume((n, n, n), 4095 if bpv == 2 else 255, 0x5EED0077)
+    return vox, (n, n, n)
+
+
+@pytest.mark.parametrize("filt", [0, 1])
+@pytest.mark.parametrize("cname", ["K0", "K1", "K2", "inside"])
+def test_empty_space_skipping_is_result_identical(filt, cname):
+    vox, dims = shells_volume()
+    cam = scenarios.camera(cname)
+    W, H = 384, 216
+    kw = dict(alpha_scale=0.08, min_val=1000, max_val=3000, filter=filt)
+    ref, cnt = oracle_frame(cam, vox, dims, 2, W, H, **kw)
+    on, st_on = run_product(vox, dims, (1, 1, 1), cam, W, H, kw, skip=vb.SKIP_ON)
+    off, st_off = run_product(vox, dims, (1, 1, 1), cam, W, H, kw, skip=vb.SKIP_OFF)
+    auto, st_auto = run_product(vox, dims, (1, 1, 1), cam, W, H, kw)
+    assert st_on.skip_used == 1 and st_off.skip_used == 0
+    assert st_auto.skip_used == 1, "AUTO should skip: most cells are empty under this window"
+    for img in (on, off, auto):
+        compare(img, ref, f"skip {filt}/{cname}")
+
+
+def test_skipping_is_refused_when_an_empty_sample_still_contributes():
+    """A transfer function whose first entry is not zero gives v = 0 samples a non-zero opacity: no skipping; a
+    negative min_val cannot be compared with unsigned cell maxima: no skipping."""
+    vox, dims = shells_volume(64)
+    cam = scenarios.camera("K1")
+    lut = scenarios.tf_lut().copy()
+    lut[0] = 0.25
+    for filt in (0, 1):
+        kw = dict(alpha_scale=0.3, min_val=1000, max_val=3000, filter=filt, tf_lut=lut)
+        ref, _ = oracle_frame(cam, vox, dims, 2, 200, 150, **kw)
+        img, st = run_product(vox, dims, (1, 1, 1), cam, 200, 150, kw, skip=vb.SKIP_ON)
+        assert st.skip_used == 0 and st.kernel_used in OPTIMISED
+        compare(img, ref, "tf lut[0] != 0")
+        kw = dict(alpha_scale=0.3, min_val=-5, max_val=3000, filter=filt)
+        ref, _ = oracle_frame(cam, vox, dims, 2, 200, 150, **kw)
+        img, st = run_product(vox, dims, (1, 1, 1), cam, 200, 150, kw, skip=vb.SKIP_ON)
+        assert st.skip_used == 0
+        compare(img, ref, "negative min_val")
+
+
+@pytest.mark.parametrize("dims,bpv", [((40, 33, 20), 1), ((70, 17, 130), 2), ((8, 8, 8), 2), ((1, 1, 1), 1), ((300, 200, 9), 2)])
+def test_cell_table_matches_numpy(dims, bpv):
+    """Per-cell min/max (SURVEY 8f-2's brick table): cell c covers voxel indices [c*2^s - 1, (c+1)*2^s - 1] per axis."""
+    rng = np.random.default_rng(5)
+    nx, ny, nz = dims
+    vox = rng.integers(0, 256 if bpv == 1 else 65536, nx * ny * nz).astype(np.uint8 if bpv == 1 else np.uint16)
+    with vb.Context(16, 16) as ctx:
+        ctx.upload_volume(vox, dims)
+        ctx.set_params(vb.default_params(min_val=100, max_val=200))
+        t = ctx.cell_table()
+    s = t["shift"]
+    assert t["cells"] == ((nx >> s) + 1, (ny >> s) + 1, (nz >> s) + 1) and s >= 3
+    v = vox.reshape(nz, ny, nx)
+    side = 1 << s
+    for cz in range(t["cells"][2]):
+        for cy in range(t["cells"][1]):
+            for cx in range(t["cells"][0]):
+                sl = tuple(slice(min(max(c * side - 1, 0), n - 1), min((c + 1) * side - 1, n - 1) + 1)
+                           for c, n in ((cz, nz), (cy, ny), (cx, nx)))
+                blk = v[sl]
+                assert t["mins"][cz, cy, cx] == blk.min() and t["maxs"][cz, cy, cx] == blk.max(), (cx, cy, cz)
+    assert t["empty_cells"] == int((t["maxs"] <= 100).sum())
+
+
+def test_volume_copies_are_built_on_demand():
+    """Footprint (VERDICT r1 weak #7): the linear copy always; each layered array only once a frame needs it."""
+    vox, dims, bpv, vs = scenarios.volume("mix_64x64x32_u16")
+    nvox = int(np.prod(dims))
+    with vb.Context(64, 64) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(scenarios.camera("K0"))
+        m = ctx.memory_info()
+        assert m["linear_bytes"] > 0 and m["array_bytes"] == 0 and m["zpair_array_bytes"] == 0
+        ctx.set_params(vb.default_params(alpha_scale=0.1, min_val=0, max_val=4095, filter=1))
+        ctx.render()
+        m = ctx.memory_info()
+        assert m["zpair_array_bytes"] == dims[0] * dims[1] * (dims[2] + 1) * 4 and m["array_bytes"] == 0
+        ctx.set_params(vb.default_params(alpha_scale=0.1, min_val=0, max_val=4095, filter=0))
+        ctx.render()
+        assert ctx.memory_info()["array_bytes"] == nvox * 2
+        ctx.upload_volume(vox, dims, vs)               # a new upload drops the derived copies
+        m = ctx.memory_info()
+        assert m["array_bytes"] == 0 and m["zpair_array_bytes"] == 0
+
+
+# ---------------------------------------------------------------- instrumentation, partitions
 
 def test_counters_and_distinct_voxels_match_oracle():
     vox, dims, bpv, vs = scenarios.volume("mix64_u8")
@@ -130,8 +331,68 @@ def test_row_tile_partition_equals_single_gpu(world, tile_rows):
     assert np.array_equal(acc.view(np.uint32), full.view(np.uint32))
 
 
+def test_rank_without_any_row_tile_renders_nothing_and_succeeds():
+    """tiles < world (H = 16, one tile of 16 rows, 2 ranks): rank 1 owns nothing; every render entry point
+    must return VR_OK instead of failing on an empty grid."""
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    W, H = 64, 16
+    with vb.Context(W, H) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(scenarios.camera("K0"))
+        ctx.set_params(vb.default_params(alpha_scale=0.1, min_val=0, max_val=255, filter=1))
+        ctx.set_partition(1, 2, 16)
+        img, st = ctx.render()
+        assert st.kernel_launches == 0 and not img.any()
+        st = ctx.render_device(0)
+        assert st.kernel_launches == 0
+        host = np.full((H, W, 4), 7.0, np.float32)
+        ctx.render_owned_to_host_ptr(host.ctypes.data)
+        assert (host == 7.0).all()
+
+
+@pytest.mark.parametrize("world,tile_rows,W,H", [(2, 16, 200, 150), (3, 4, 200, 150), (8, 16, 200, 150), (2, 8, 1280, 720), (4, 8, 1000, 500)])
+def test_owned_tiles_to_host_frame_assemble_the_frame(world, tile_rows, W, H):
+    """Multi-GPU end to end (vr_render_owned_to_host): every rank copies only its own row tiles into a
+    full host frame; all ranks together (emulated on one device) reproduce the unpartitioned frame.  The
+    larger frames take the banded path (copies overlap the march of the following bands)."""
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    kw = dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)
+    full, _ = run_product(vox, dims, vs, cam, W, H, kw)
+    host = np.full((H, W, 4), np.nan, dtype=np.float32)
+    with vb.Context(W, H) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(cam)
+        ctx.set_params(vb.default_params(**kw))
+        for rank in range(world):
+            ctx.set_partition(rank, world, tile_rows)
+            before = host.copy()
+            st = ctx.render_owned_to_host_ptr(host.ctypes.data)
+            assert st.kernel_launches >= 1
+            owned = ((np.arange(H) // tile_rows) % world) == rank
+            # rows of other ranks are untouched
+            assert np.array_equal(host[~owned].view(np.uint32), before[~owned].view(np.uint32))
+    assert np.array_equal(host.view(np.uint32), full.view(np.uint32))
+
+
+@pytest.mark.parametrize("W,H", [(131, 67), (1, 5), (65, 8), (1280, 724)])
+def test_odd_image_sizes_and_banded_frames(W, H):
+    """Widths below one CTA tile, heights that are not a multiple of the tile, and a frame large enough for the
+    banded host copy."""
+    vox, dims, bpv, vs = scenarios.volume("mix_64x64x32_u16")
+    cam = scenarios.camera("K1")
+    for filt in (0, 1):
+        kw = dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=filt)
+        ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
+        img, st = run_product(vox, dims, vs, cam, W, H, kw)
+        assert st.kernel_used == expected_kernel(kw)
+        compare(img, ref, f"{W}x{H} filter {filt}")
+
+
+# ---------------------------------------------------------------- ingest
+
 def test_volume_stats_match_reference_loops():
-    """min/max + histogram kernels vs a numpy restatement of RendererCore.cpp:360-405."""
+    """fused pad + min/max kernel and the histogram kernel vs a numpy restatement of RendererCore.cpp:360-405."""
     rng = np.random.default_rng(3)
     # (51, 41, 31): odd voxel count -> the scalar tail behind the 16-byte vector body; 65535: full u16 range
     for bpv, hi, dims in ((1, 256, (50, 40, 30)), (2, 3000, (50, 40, 30)), (1, 256, (51, 41, 31)), (2, 65536, (51, 41, 31))):
@@ -211,172 +472,8 @@ def test_error_paths():
         with pytest.raises(vb.VolrenError):
             ctx.set_params(vb.default_params(step_scale=0.0))
         with pytest.raises(vb.VolrenError):
+            ctx.set_params(vb.default_params(kernel=3))     # a round-1 development kernel
+        with pytest.raises(vb.VolrenError):
+            ctx.set_params(vb.default_params(empty_skip=7))
+        with pytest.raises(vb.VolrenError):
             ctx.set_partition(2, 2, 8)
-
-
-def test_full_size_1024_cube_sampled_rows():
-    """BASELINE's headline size (1024^3 uint16, 1920x1080, 1024 steps): the oracle renders
-    every 60th row of the same volume; those rows must match bit for bit.  Also checks the
-    size-independent property N-GPU == 1-GPU on the full frame."""
-    import torch
-    from volren_b200 import workloads
-    dims, W, H = (1024, 1024, 1024), 1920, 1080
-    cam = scenarios.camera("K2")
-    kw = dict(alpha_scale=0.02, min_val=0, max_val=4095, filter=1)
-    with vb.Context(W, H) as ctx:
-        copy = torch.empty(1024 ** 3, dtype=torch.int16, device="cuda")
-        ctx.upload_synthetic(dims, 2, 4095, workloads.SEEDS["C4"], True, copy_out_dptr=copy.data_ptr())
-        host = copy.cpu().numpy().view(np.uint16)
-        del copy
-        ctx.set_camera(cam)
-        ctx.set_params(vb.default_params(**kw))
-        img, st = ctx.render()
-        for kernel in (vb.KERNEL_DIRECT, vb.KERNEL_WINDOWED, vb.KERNEL_FAST, vb.KERNEL_TEXGATHER, vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU):      # every kernel, same bits, at full size
-            ctx.set_params(vb.default_params(kernel=kernel, **kw))
-            other, st2 = ctx.render()
-            assert st2.kernel_used == kernel
-            assert np.array_equal(other.view(np.uint32), img.view(np.uint32))
-        ctx.set_params(vb.default_params(**kw))
-        # 2-way partition of the same frame
-        acc = np.zeros_like(img)
-        for rank in range(2):
-            ctx.set_partition(rank, 2, 8)
-            part, _ = ctx.render()
-            owned = ((np.arange(H) // 8) % 2) == rank
-            acc[owned] = part[owned]
-    assert np.array_equal(acc.view(np.uint32), img.view(np.uint32))
-    p = orc.make_params(W, H, dims, 2, cam, row_begin=7, row_stride=60, **kw)
-    ref, cnt, _ = orc.render(p, host, nthreads=16)
-    rows = np.arange(7, H, 60)
-    compare(img[rows], ref[rows], "1024^3 sampled rows")
-    assert cnt["rays_hit"] > 0.8 * rows.size * W   # K2: the volume covers ~85 % of the frame
-
-
-@pytest.mark.parametrize("W,H", [(131, 67), (1, 5), (65, 8)])
-def test_texpair_odd_image_sizes(W, H):
-    """Two rays per thread: odd widths (the last thread of a row owns one pixel), widths below one
-    CTA tile, and pairs whose rays leave the box at different steps (oblique camera)."""
-    vox, dims, bpv, vs = scenarios.volume("mix_64x64x32_u16")
-    cam = scenarios.camera("K1")
-    kw = dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1)
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
-    for kernel in (vb.KERNEL_TEXPAIR, vb.KERNEL_TEXPAIR2, vb.KERNEL_TEXPAIR_PIPE, vb.KERNEL_HYBRID, vb.KERNEL_ZLSU):
-        img, st = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
-        assert st.kernel_used == kernel
-        compare(img, ref, f"texpair {W}x{H} kernel{kernel}")
-
-
-@pytest.mark.parametrize("vname,cname,kw", [
-    ("mix64_u8", "K1", dict(alpha_scale=0.3, min_val=0, max_val=255, filter=1, tf=True)),
-    ("mix64_u8", "K2", dict(alpha_scale=0.08, min_val=30, max_val=200, filter=1, tf=True, step_scale=0.5)),
-    ("mix_64x64x32_u16", "K1", dict(alpha_scale=0.2, min_val=100, max_val=3900, filter=1, tf=True)),
-    ("rand_40x56x33_u16", "K2", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1, tf=True)),
-])
-def test_transfer_function_runs_on_the_pipelined_gather_kernel(vname, cname, kw):
-    """CubicSpline transfer function (BASELINE config 3): the opacity LUT is read inside the optimised
-    kernel -- no fallback to the generic DIRECT loop -- and the frame equals the oracle's bit for bit."""
-    vox, dims, bpv, vs = scenarios.volume(vname)
-    cam = scenarios.camera(cname)
-    W, H = 320, 200
-    okw, vkw = scenarios.split_kwargs(kw)
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
-    img, st = run_product(vox, dims, vs, cam, W, H, vkw)
-    assert st.kernel_used == vb.KERNEL_TEXPAIR_PIPE
-    compare(img, ref, f"tf {vname}/{cname}")
-    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
-    assert st2.kernel_used == vb.KERNEL_DIRECT
-    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
-
-
-@pytest.mark.parametrize("vname,cname,kw", [
-    ("mix_64x64x32_u16", "K2", dict(alpha_scale=1.0, min_val=1000, max_val=3000, filter=1, is_mip=1)),
-    ("mix64_u8", "K1", dict(alpha_scale=0.6, min_val=0, max_val=255, filter=1, is_mip=1)),
-    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.9, min_val=0, max_val=4095, filter=1, is_mip=1, step_scale=0.5)),
-])
-def test_mip_runs_on_the_pipelined_gather_kernel(vname, cname, kw):
-    """MIP (VolumeRenderer.cs:141-173, the GUI's use_mip toggle) with the trilinear filter runs in the
-    optimised kernel and equals the oracle and the generic DIRECT loop bit for bit."""
-    vox, dims, bpv, vs = scenarios.volume(vname)
-    cam = scenarios.camera(cname)
-    W, H = 320, 200
-    okw, vkw = scenarios.split_kwargs(kw)
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
-    img, st = run_product(vox, dims, vs, cam, W, H, vkw)
-    assert st.kernel_used == vb.KERNEL_TEXPAIR_PIPE
-    compare(img, ref, f"mip {vname}/{cname}")
-    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
-    assert st2.kernel_used == vb.KERNEL_DIRECT
-    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
-
-
-@pytest.mark.parametrize("world,tile_rows", [(2, 16), (3, 4), (8, 16)])
-def test_owned_tiles_to_host_frame_assemble_the_frame(world, tile_rows):
-    """Multi-GPU end to end (vr_render_owned_to_host): every rank copies only its own row tiles into a
-    full host frame; all ranks together (emulated on one device) reproduce the unpartitioned frame."""
-    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
-    cam = scenarios.camera("K1")
-    W, H = 200, 150
-    kw = dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1)
-    full, _ = run_product(vox, dims, vs, cam, W, H, kw)
-    host = np.full((H, W, 4), np.nan, dtype=np.float32)
-    with vb.Context(W, H) as ctx:
-        ctx.upload_volume(vox, dims, vs)
-        ctx.set_camera(cam)
-        ctx.set_params(vb.default_params(**kw))
-        for rank in range(world):
-            ctx.set_partition(rank, world, tile_rows)
-            before = host.copy()
-            st = ctx.render_owned_to_host_ptr(host.ctypes.data)
-            assert st.kernel_launches >= 1
-            owned = ((np.arange(H) // tile_rows) % world) == rank
-            # rows of other ranks are untouched
-            assert np.array_equal(host[~owned].view(np.uint32), before[~owned].view(np.uint32))
-    assert np.array_equal(host.view(np.uint32), full.view(np.uint32))
-
-
-@pytest.mark.parametrize("vname,cname,kw", [
-    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=0, max_val=255, filter=1, view_top=1)),
-    ("rand_40x56x33_u16", "K0", dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1, view_bottom=1)),
-    ("mix_64x64x32_u16", "K2", dict(alpha_scale=0.05, min_val=1000, max_val=3000, filter=1, view_top=1)),
-    ("mix64_u8", "K1", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1, view_bottom=1, step_scale=0.5)),
-    ("mix64_u8", "K2", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=1, view_top=1, view_bottom=1)),   # top wins (:183)
-])
-def test_view_swizzles_run_on_the_pipelined_gather_kernel(vname, cname, kw):
-    """rotate_to_top / rotate_to_bottom (VolumeRenderer.cs:68-78,183-190) with the trilinear filter run
-    in the optimised kernel and equal the oracle and the generic DIRECT loop bit for bit."""
-    vox, dims, bpv, vs = scenarios.volume(vname)
-    cam = scenarios.camera(cname)
-    W, H = 320, 200
-    okw, vkw = scenarios.split_kwargs(kw)
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **okw)
-    img, st = run_product(vox, dims, vs, cam, W, H, vkw)
-    assert st.kernel_used == vb.KERNEL_TEXPAIR_PIPE
-    compare(img, ref, f"view {vname}/{cname}")
-    direct, st2 = run_product(vox, dims, vs, cam, W, H, vkw, kernel=vb.KERNEL_DIRECT)
-    assert st2.kernel_used == vb.KERNEL_DIRECT
-    assert np.array_equal(direct.view(np.uint32), img.view(np.uint32))
-
-
-@pytest.mark.parametrize("vname,cname,kw", [
-    ("mix64_u8", "K0", dict(alpha_scale=0.05, min_val=0, max_val=255, filter=0)),
-    ("mix64_u8", "K2", dict(alpha_scale=1.0, min_val=40, max_val=200, filter=0)),
-    ("rand_48x40x36_u8", "K1", dict(alpha_scale=0.08, min_val=10, max_val=250, filter=0)),
-    ("mix_64x64x32_u16", "K0", dict(alpha_scale=0.5, min_val=1000, max_val=3000, filter=0)),
-    ("rand_40x56x33_u16", "orbit", dict(alpha_scale=0.03, min_val=0, max_val=4095, filter=0, step_scale=0.5)),
-    ("full_u16", "K1", dict(alpha_scale=0.04, min_val=0, max_val=65535, filter=0)),
-    ("one_voxel_u8", "K0", dict(alpha_scale=0.7, min_val=0, max_val=255, filter=0)),
-])
-def test_nearest_filter_runs_on_the_texel_load_kernel(vname, cname, kw):
-    """The de-facto reference filter (integer texture => nearest texel): AUTO runs the pipelined
-    texel-load kernel, bit-identical to the oracle and to the FAST and DIRECT kernels."""
-    vox, dims, bpv, vs = scenarios.volume(vname)
-    cam = scenarios.camera(cname)
-    W, H = 320, 200
-    ref, _ = oracle_frame(cam, vox, dims, bpv, W, H, voxel_size=vs, **kw)
-    img, st = run_product(vox, dims, vs, cam, W, H, kw)
-    assert st.kernel_used == vb.KERNEL_NEAREST_TEX
-    compare(img, ref, f"nearest {vname}/{cname}")
-    for kernel in (vb.KERNEL_FAST, vb.KERNEL_DIRECT):
-        other, st2 = run_product(vox, dims, vs, cam, W, H, kw, kernel=kernel)
-        assert st2.kernel_used == kernel
-        assert np.array_equal(other.view(np.uint32), img.view(np.uint32))

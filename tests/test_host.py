@@ -272,3 +272,52 @@ def test_frame_constants_match_the_oracle_bit_for_bit():
         assert np.array_equal(mine[16:19], (np.float32(1.0) / mine[9:12]).astype(np.float32)), what
         pow2 = all(float(d) > 0 and np.frexp(float(d))[0] == 0.5 for d in mine[9:12])
         assert int(mine[20]) == (0 if pow2 else 1), what
+
+
+# ------------------------------------------------------------------ .raw mmap path, 64-bit sizes, untrusted headers
+
+def test_raw_payload_is_memory_mapped_with_64_bit_offsets(tmp_path):
+    """SURVEY 8f-3: the reference reads a .raw through `int len` (RendererCore.cpp:327) and fails above 2^31 voxels;
+    here the payload is mapped read-only.  A sparse 5 GiB file costs no disk space; bytes beyond 4 GiB are reachable."""
+    fn = str(tmp_path / "big.raw")
+    size = 5 * (1 << 30) + 123
+    with open(fn, "wb") as f:
+        f.truncate(size)
+        f.seek((1 << 32) + 17); f.write(b"\xAB")
+        f.seek(size - 1); f.write(b"\xCD")
+    m = host.MappedRaw(fn)
+    assert m.size == size
+    assert m.byte((1 << 32) + 17) == 0xAB and m.byte(size - 1) == 0xCD and m.byte(12345) == 0
+    assert m.byte(size) == -1
+    with pytest.raises(OSError):
+        host.MappedRaw(str(tmp_path / "missing.raw"))
+
+
+def test_volume_byte_counts_are_overflow_checked():
+    """untrusted dimensions are range checked before they are multiplied."""
+    assert host.checked_volume_bytes((2048, 2048, 1024), 2) == 8 << 30
+    assert host.checked_volume_bytes((16384, 16384, 16384), 2) == 1 << 43
+    for bad in ((0, 4, 4), (16385, 1, 1), (1 << 31, 1 << 31, 4), (2 ** 32 - 1, 2 ** 32 - 1, 2 ** 32 - 1)):
+        assert host.checked_volume_bytes(bad, 2) is None
+    assert host.checked_volume_bytes((4, 4, 4), 0) is None
+
+
+def test_pvm_header_with_hostile_dimensions_is_rejected():
+    """A PVM header whose width*height*depth*components wraps 64 bits must not pass the payload-length check."""
+    for dims in (b"4294967295 4294967295 4294967295", b"2147483648 2147483648 4", b"16385 1 1"):
+        blob = b"PVM\n" + dims + b"\n1\n" + b"\x00" * 64
+        p = host.pvm_decode(data=blob)
+        assert not p["ok"], dims
+    assert "16384" in host.pvm_decode(data=b"PVM\n16385 1 1\n1\n" + b"\x00" * 64)["error"]
+
+
+def test_read_volume_data_reports_bad_inf_dimensions_without_throwing(tmp_path):
+    """A .raw.inf with absurd dimensions must end in a popup (title/msg), not in bad_alloc through the C boundary."""
+    fn = str(tmp_path / "v.raw")
+    open(fn, "wb").write(b"\x00" * 64)
+    open(fn + ".inf", "w").write("#dimensions\n2000000000 2000000000 2000000000\n\n#voxel-spacing\n1 1 1\n")
+    core = host.RendererCore(64, 64)
+    core.set_datasize_bytes(1)
+    core.readVolumeData(fn)                  # no GPU needed: fails before any upload
+    st = core.strings()
+    assert st["title"] == "Invalid Data Size!" and "16384" in st["msg"]

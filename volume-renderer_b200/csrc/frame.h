@@ -25,6 +25,7 @@ struct FrameConsts {
     int32_t W, H;
     int32_t rank, world, tile_rows;
     int32_t compact;              // 1: output holds owned rows only, packed
+    int32_t row0;                 // first local (owned) row of this launch: a band of the partition
     // camera block (Camera::setUBO, Camera.cpp:59-80)
     float cam[21];
     // bounding box, VolumeRenderer.cs:62-83

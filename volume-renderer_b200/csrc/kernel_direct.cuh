@@ -28,7 +28,7 @@ march_direct_kernel(const __grid_constant__ FrameConsts fc, const __grid_constan
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = blockIdx.x * DIRECT_BLOCK_W + (warp & 3) * 8 + (lane & 7);
-    const int lrow = blockIdx.y * DIRECT_BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
+    const int lrow = fc.row0 + blockIdx.y * DIRECT_BLOCK_H + (warp >> 2) * 4 + (lane >> 3);
     if (px >= fc.W || lrow >= args.local_rows) return;
     const int py = owned_row_to_global(fc, lrow);
     if (py >= fc.H) return;

@@ -1,5 +1,6 @@
 // kernels_aux.cuh -- HBM-bound helper kernels either side of the march:
-// volume ingest (edge-replicated padding, min/max, histogram), synthetic volume generation,
+// volume ingest (edge-replicated padding fused with min/max, histogram, z-pair words, per-cell min/max table),
+// synthetic volume generation,
 // divisor verification, tile assembly after the multi-GPU gather, RGB8 read-back, popcount.
 #pragma once
 
@@ -10,14 +11,17 @@
 
 namespace vr {
 
-// ---- ingest: linear x-fastest volume -> edge-replicated padded volume --------------------
-// One thread per 4 padded voxels along x; grid-stride over rows.  Replaces what the GL driver
-// does inside glTexImage3D + GL_CLAMP_TO_EDGE (RendererCore.cpp:408-419).
+// ---- ingest: linear x-fastest volume -> edge-replicated padded volume, fused with the min/max scan ----
+// ONE read of the source: a block per padded row (grid-stride), a thread per padded voxel along x.
+// Replaces what the GL driver does inside glTexImage3D + GL_CLAMP_TO_EDGE (RendererCore.cpp:408-419)
+// and the reference's single-threaded min/max loop (RendererCore.cpp:362-379); every source voxel
+// appears in at least one padded row, so the running min/max over what is copied is the volume's.
 template <typename T>
-__global__ void pad_volume_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                  int nx, int ny, int nz, uint32_t pitch)
+__global__ void pad_minmax_kernel(const T* __restrict__ src, T* __restrict__ dst, int nx, int ny, int nz, uint32_t pitch,
+                                  unsigned int* out_min, unsigned int* out_max)
 {
     const uint64_t rows = (uint64_t)(ny + 2) * (uint64_t)(nz + 2);
+    unsigned int lo = 0xffffffffu, hi = 0u;
     for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const int jz = (int)(row / (uint64_t)(ny + 2));
         const int jy = (int)(row - (uint64_t)jz * (uint64_t)(ny + 2));
@@ -26,96 +30,89 @@ __global__ void pad_volume_kernel(const T* __restrict__ src, T* __restrict__ dst
         T* d = dst + row * (uint64_t)pitch;
         for (uint32_t jx = threadIdx.x; jx < pitch; jx += blockDim.x) {
             const int x = min(max((int)jx - 1, 0), nx - 1);
-            d[jx] = s[x];
+            const unsigned int v = s[x];
+            d[jx] = (T)v;
+            lo = min(lo, v); hi = max(hi, v);
         }
     }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
 }
 
-// ---- ingest: pair-packed variant of the padded volume: word x = (voxel x, voxel x+1) ------------
+// ---- z-pair words for the texpair kernel, derived from the padded volume -----------------------------
+// Layers [l0, l0+nl) of the z-pair array into a tightly packed staging buffer: word (x, y, L) =
+// v(x, y, max(L-1,0)) | v(x, y, min(L,nz-1)) << bits = padded(x+1, y+1, L) | padded(x+1, y+1, L+1) << bits.
+// L runs over [0, nz]: layer iz+1 of a sample with iz = floor(fz) in [-1, nz-1] holds both z slices of its
+// trilinear footprint, GL_CLAMP_TO_EDGE in z already applied (RendererCore.cpp:413).
 template <typename T, typename W>
-__global__ void pad_pairs_kernel(const T* __restrict__ src, W* __restrict__ dst, int nx, int ny, int nz, uint32_t pitch)
-{
-    const uint64_t rows = (uint64_t)(ny + 2) * (uint64_t)(nz + 2);
-    for (uint64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int jz = (int)(row / (uint64_t)(ny + 2));
-        const int jy = (int)(row - (uint64_t)jz * (uint64_t)(ny + 2));
-        const int y = min(max(jy - 1, 0), ny - 1), z = min(max(jz - 1, 0), nz - 1);
-        const T* s = src + ((uint64_t)z * ny + y) * (uint64_t)nx;
-        W* d = dst + row * (uint64_t)pitch;
-        for (uint32_t jx = threadIdx.x; jx < pitch; jx += blockDim.x) {
-            const int x0 = min(max((int)jx - 1, 0), nx - 1), x1 = min(max((int)jx, 0), nx - 1);
-            d[jx] = (W)((W)s[x0] | ((W)s[x1] << (8 * sizeof(T))));
-        }
-    }
-}
-
-// ---- ingest: z-pair words for the texpair kernel ------------------------------------------------
-// Layers [l0, l0+nl) of the z-pair array: word (x, y, L) = v(x, y, max(L-1,0)) | v(x, y, min(L,nz-1)) << bits.
-// L runs over [0, nz]: the layer iz+1 of a sample with iz = floor(fz) in [-1, nz-1] holds both z slices
-// of its trilinear footprint, GL_CLAMP_TO_EDGE in z already applied (RendererCore.cpp:413).
-template <typename T, typename W>
-__global__ void zpair_pack_kernel(const T* __restrict__ src, W* __restrict__ dst, int nx, int ny, int nz, int l0, int nl)
+__global__ void zpair_pack_kernel(const T* __restrict__ padded, W* __restrict__ dst, int nx, int ny, uint32_t pitch,
+                                  uint64_t slice, int l0, int nl)
 {
     const uint64_t per_layer = (uint64_t)nx * ny, n = per_layer * (uint64_t)nl;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const int L = l0 + (int)(i / per_layer);
         const uint64_t xy = i % per_layer;
-        const int za = max(L - 1, 0), zb = min(L, nz - 1);
-        dst[i] = (W)((W)src[(uint64_t)za * per_layer + xy] | ((W)src[(uint64_t)zb * per_layer + xy] << (8 * sizeof(T))));
+        const uint32_t y = (uint32_t)(xy / (uint64_t)nx), x = (uint32_t)(xy - (uint64_t)y * nx);
+        const uint64_t e = (uint64_t)L * slice + (uint64_t)(y + 1) * pitch + (x + 1);
+        dst[i] = (W)((W)padded[e] | ((W)padded[e + slice] << (8 * sizeof(T))));
     }
 }
 
-// Linear copy of the same z-pair words for the LSU stage of the hybrid lab kernels, derived from the
-// padded volume (same pitch): word i = padded[i] | padded[i + slice] << bits, i over (nz+1) slices.
-template <typename T, typename W>
-__global__ void zpair_from_padded_kernel(const T* __restrict__ padded, W* __restrict__ dst, uint64_t slice, uint64_t nwords)
-{
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (uint64_t)gridDim.x * blockDim.x)
-        dst[i] = (W)((W)padded[i] | ((W)padded[i + slice] << (8 * sizeof(T))));
-}
-
-// ---- ingest: min/max scan (RendererCore.cpp:362-379) --------------------------------------
-// HBM-bound read of the whole volume: 16-byte loads (8 u16 / 16 u8 per thread and request), four
-// requests in flight per thread, scalar head/tail for unaligned ends.
+// ---- per-cell min/max table (the brick table of SURVEY 8f-2) and the empty-cell map ------------------
+// Cell (cx,cy,cz) of side 2^shift covers, on each axis, the voxel indices [c*2^shift - 1, (c+1)*2^shift - 1]
+// clamped to the volume: exactly the voxels a sample whose base index i0 satisfies (i0+1) >> shift == c can
+// touch (trilinear footprint {i0, i0+1} after GL_CLAMP_TO_EDGE; the nearest voxel is i0 itself).  One CTA per
+// cell, grid-stride; a warp per (y,z) row of the cell, lanes along x.
 template <typename T>
-__device__ __forceinline__ void minmax_word(uint32_t w, unsigned int& lo, unsigned int& hi)
+__global__ void __launch_bounds__(128)
+cell_minmax_kernel(const T* __restrict__ padded, uint32_t pitch, uint64_t slice, int nx, int ny, int nz, int shift,
+                   int cnx, int cny, int cnz, uint16_t* __restrict__ cmin, uint16_t* __restrict__ cmax)
 {
-    if (sizeof(T) == 2) {
-        const unsigned int a = w & 0xffffu, b = w >> 16;
-        lo = min(lo, min(a, b)); hi = max(hi, max(a, b));
-    } else {
-        const unsigned int a = w & 0xffu, b = (w >> 8) & 0xffu, c = (w >> 16) & 0xffu, d = w >> 24;
-        lo = min(min(lo, min(a, b)), min(c, d)); hi = max(max(hi, max(a, b)), max(c, d));
+    __shared__ unsigned int s_lo[4], s_hi[4];
+    const int side = 1 << shift, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t ncells = (uint64_t)cnx * cny * cnz;
+    for (uint64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+        const int cx = (int)(cell % (uint64_t)cnx), cy = (int)((cell / (uint64_t)cnx) % (uint64_t)cny), cz = (int)(cell / ((uint64_t)cnx * cny));
+        // padded index = voxel index + 1; the padding replicates the edge, so the clamp is only needed to stay in bounds
+        const int x0 = cx * side, x1 = min((cx + 1) * side, nx + 1);       // padded x range [x0, x1]
+        const int y0 = cy * side, y1 = min((cy + 1) * side, ny + 1);
+        const int z0 = cz * side, z1 = min((cz + 1) * side, nz + 1);
+        unsigned int lo = 0xffffffffu, hi = 0u;
+        const int rows_y = y1 - y0 + 1, nrows = rows_y * (z1 - z0 + 1);
+        for (int r = warp; r < nrows; r += 4) {
+            const int jz = z0 + r / rows_y, jy = y0 + r % rows_y;
+            const T* row = padded + (uint64_t)jz * slice + (uint64_t)jy * pitch;
+            for (int jx = x0 + lane; jx <= x1; jx += 32) { const unsigned int v = row[jx]; lo = min(lo, v); hi = max(hi, v); }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cmin[cell] = (uint16_t)min(min(s_lo[0], s_lo[1]), min(s_lo[2], s_lo[3]));
+            cmax[cell] = (uint16_t)max(max(s_hi[0], s_hi[1]), max(s_hi[2], s_hi[3]));
+        }
+        __syncthreads();
     }
 }
 
-template <typename T>
-__global__ void minmax_kernel(const T* __restrict__ src, uint64_t n, unsigned int* out_min, unsigned int* out_max)
+// bit c of the map = (cell max <= threshold); one warp ballot per 32 cells; counts the empty cells.
+// Launch with a whole number of warps covering ceil(ncells / 32) * 32 cells.
+__global__ void cell_empty_kernel(const uint16_t* __restrict__ cmax, uint64_t ncells, unsigned int threshold,
+                                  uint32_t* __restrict__ bits, unsigned long long* count)
 {
-    unsigned int lo = 0xffffffffu, hi = 0u;
-    constexpr uint64_t PER = 16 / sizeof(T);
-    const uint64_t head = min(n, (uint64_t)(((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) / sizeof(T)));
-    const uint64_t nvec = (n - head) / PER;
-    const uint4* __restrict__ v = reinterpret_cast<const uint4*>(src + head);
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = tid;
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        const uint4 a = __ldg(v + i), b = __ldg(v + i + stride), c = __ldg(v + i + 2 * stride), d = __ldg(v + i + 3 * stride);
-        minmax_word<T>(a.x, lo, hi); minmax_word<T>(a.y, lo, hi); minmax_word<T>(a.z, lo, hi); minmax_word<T>(a.w, lo, hi);
-        minmax_word<T>(b.x, lo, hi); minmax_word<T>(b.y, lo, hi); minmax_word<T>(b.z, lo, hi); minmax_word<T>(b.w, lo, hi);
-        minmax_word<T>(c.x, lo, hi); minmax_word<T>(c.y, lo, hi); minmax_word<T>(c.z, lo, hi); minmax_word<T>(c.w, lo, hi);
-        minmax_word<T>(d.x, lo, hi); minmax_word<T>(d.y, lo, hi); minmax_word<T>(d.z, lo, hi); minmax_word<T>(d.w, lo, hi);
+    const uint64_t words = (ncells + 31) / 32;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned int n = 0;
+    for (uint64_t w = warp; w < words; w += nwarps) {
+        const uint64_t i = w * 32 + lane;
+        const bool e = i < ncells && (unsigned int)cmax[i] <= threshold;
+        const unsigned int m = __ballot_sync(0xffffffffu, e);
+        if (lane == 0) { bits[w] = m; n += __popc(m); }
     }
-    for (; i < nvec; i += stride) {
-        const uint4 a = __ldg(v + i);
-        minmax_word<T>(a.x, lo, hi); minmax_word<T>(a.y, lo, hi); minmax_word<T>(a.z, lo, hi); minmax_word<T>(a.w, lo, hi);
-    }
-    // scalar head and tail
-    for (uint64_t k = tid; k < head; k += stride) { const unsigned int x = src[k]; lo = min(lo, x); hi = max(hi, x); }
-    for (uint64_t k = head + nvec * PER + tid; k < n; k += stride) { const unsigned int x = src[k]; lo = min(lo, x); hi = max(hi, x); }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
+    if (lane == 0 && n) atomicAdd(count, (unsigned long long)n);
 }
 
 // ---- ingest: 256-bin histogram (RendererCore.cpp:386-398) ---------------------------------
@@ -283,11 +280,17 @@ __global__ void peer_signal_kernel(unsigned int* sync)
     atomicAdd_system(&sync[0], 1u);
 }
 // word `idx` of `sync` >= target (wrap-safe), else error after timeout_ns
-__global__ void peer_wait_kernel(unsigned int* sync, int idx, unsigned int target, unsigned long long timeout_ns)
+// (`host_error`: a word of mapped pinned host memory the next ABI call checks without synchronising)
+__global__ void peer_wait_kernel(unsigned int* sync, int idx, unsigned int target, unsigned long long timeout_ns,
+                                 volatile unsigned int* host_error)
 {
     const unsigned long long t0 = global_ns();
     while ((int)(ld_acquire_sys(&sync[idx]) - target) < 0) {
-        if (global_ns() - t0 > timeout_ns) { atomicExch_system(&sync[2], 1u); break; }
+        if (global_ns() - t0 > timeout_ns) {
+            atomicExch_system(&sync[2], 1u);
+            if (host_error) { *host_error = 1u + (unsigned int)idx; __threadfence_system(); }
+            break;
+        }
         __nanosleep(64);
     }
     __threadfence_system();

@@ -19,8 +19,7 @@
 #include "frame.h"
 #include "march_device.cuh"
 #include "kernel_direct.cuh"
-#include "kernel_fast.cuh"
-#include "kernel_windowed.cuh"
+#include "kernel_march.cuh"
 #include "kernels_aux.cuh"
 
 namespace {
@@ -53,6 +52,46 @@ inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 constexpr size_t FRAME_SYNC_BYTES = 256;
 inline size_t frame_alloc_bytes(int w, int h) { return (size_t)w * h * 4 * sizeof(float) + FRAME_SYNC_BYTES; }
 
+// device allocation released on scope exit unless handed over (upload error paths must not leak)
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    void* release() { void* q = p; p = nullptr; return q; }
+    template <typename U> U* as() const { return static_cast<U*>(p); }
+};
+
+// pipeline depth / resident CTAs per SM of the optimised kernels, measured on the headline frame
+// (lab r2: depth 3 at 64 registers / 4 CTAs per SM is the most robust choice across cameras, partitions, volume
+// shapes; the skipping forms carry the leap state and want the same register budget)
+#ifndef VR_TP_DEPTH
+#define VR_TP_DEPTH 3
+#endif
+#ifndef VR_TP_MINB
+#define VR_TP_MINB 4
+#endif
+#ifndef VR_TP_SKIP_DEPTH
+#define VR_TP_SKIP_DEPTH 2
+#endif
+#ifndef VR_TP_SKIP_MINB
+#define VR_TP_SKIP_MINB 4
+#endif
+#ifndef VR_NN_DEPTH
+#define VR_NN_DEPTH 2
+#endif
+#ifndef VR_NN_MINB
+#define VR_NN_MINB 8      // the capless nearest loop fits 32 registers
+#endif
+#ifndef VR_NN_SKIP_DEPTH
+#define VR_NN_SKIP_DEPTH 2
+#endif
+#ifndef VR_NN_SKIP_MINB
+#define VR_NN_SKIP_MINB 5
+#endif
+
 }  // namespace
 
 struct vr_context {
@@ -61,25 +100,30 @@ struct vr_context {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float* d_frame = nullptr;            // W*H*4
+    float* d_frame = nullptr;            // W*H*4 (+ barrier words)
     uint8_t* d_rgb8 = nullptr;           // W*H*3
-    // volume (padded, edge replicated)
+    // volume: edge-replicated linear copy (always), layered arrays built on first use
     void* d_vol = nullptr;
     uint64_t vol_bytes = 0;
     int32_t dim[3] = {0, 0, 0};
     int bpv = 0;
     uint32_t pitch = 0;                  // elements
     uint64_t slice = 0;                  // elements
-    // second copy for the texture-gather kernel: layered 2-D array (layer = z), point sampling
-    cudaArray_t d_arr = nullptr;
+    cudaArray_t d_arr = nullptr;         // source-type layered array (layer = z), point sampling: NEAREST_TEX
     cudaTextureObject_t tex = 0;
-    // third copy for the z-pair gather kernel: layered 2-D array of (z, z+1) words, Nz+1 layers
-    cudaArray_t d_arr2 = nullptr;
+    bool arr_failed = false;
+    cudaArray_t d_arr2 = nullptr;        // z-pair layered array, Nz+1 layers: TEXPAIR_PIPE
     cudaTextureObject_t tex2 = 0;
-    // ... and the same words as a linear edge-replicated array for the LSU stage of the hybrid kernel
-    void* d_zlin = nullptr;
-    uint32_t zpitch = 0;                 // words
-    uint64_t zslice = 0;                 // words
+    bool arr2_failed = false;
+    // per-cell min/max table + empty map for the current min_val
+    uint16_t* d_cell_min = nullptr;
+    uint16_t* d_cell_max = nullptr;
+    uint32_t* d_cell_bits = nullptr;      // empty-cell bit map for `empty_thresh`
+    unsigned long long* d_cell_count = nullptr;
+    int cell_shift = 0, cells[3] = {0, 0, 0};
+    uint64_t ncells = 0, empty_cells = 0;
+    bool empty_valid = false;
+    int32_t empty_thresh = 0;
     float voxel_size[3] = {1.f, 1.f, 1.f};
     vr_volume_stats stats{};
     bool have_stats = false;
@@ -87,16 +131,17 @@ struct vr_context {
     float cam[21];
     bool have_cam = false;
     vr_params params;
-    float* d_lut = nullptr;
+    float* d_lut = nullptr;              // [0,256): the caller's LUT; [256,512): host-finalised opacity
     bool lut_fast_ok = false;            // every LUT entry finite and >= +0
     int rank = 0, world = 1, tile_rows = 8;
     // Markstein verification cache: divisor bits -> ok
     std::map<uint32_t, bool> div_ok;
     unsigned int* d_flag = nullptr;
-    // windowed kernel scratch
-    vr::WindowedState win;
-    // vr_render to a host buffer: row bands on their own streams so a band's device->host copy
-    // overlaps the march of the following bands
+    // fused peer hand-off
+    unsigned int* d_done = nullptr;      // CTAs finished (march kernel epilogue)
+    unsigned int* h_peer_error = nullptr;   // mapped pinned word: a barrier wait gave up
+    unsigned int* d_peer_error = nullptr;
+    // row bands on their own streams: a band's device->host copy overlaps the march of the following bands
     static constexpr int BANDS = 4;
     cudaStream_t band_stream[BANDS] = {};
     cudaEvent_t band_kdone[BANDS] = {}, band_cdone[BANDS] = {};
@@ -105,23 +150,11 @@ struct vr_context {
 
 namespace {
 
-int owned_rows_of(int H, int rank, int world, int tile_rows)
-{
-    const int tiles = (H + tile_rows - 1) / tile_rows;
-    int rows = 0;
-    for (int t = rank; t < tiles; t += world) {
-        const int y0 = t * tile_rows;
-        rows += std::min(tile_rows, H - y0);
-    }
-    return rows;
-}
-
 // rows of the compact image: every owned tile padded to tile_rows (keeps the gather regular)
 int compact_rows_of(int H, int rank, int world, int tile_rows)
 {
     const int tiles = (H + tile_rows - 1) / tile_rows;
-    const int owned_tiles = (tiles - rank + world - 1) / world;
-    (void)rank;
+    const int owned_tiles = tiles > rank ? (tiles - rank + world - 1) / world : 0;
     return owned_tiles * tile_rows;
 }
 
@@ -148,11 +181,121 @@ int verify_divisor(vr_context* c, float d, bool* ok)
     return VR_OK;
 }
 
+// ---- layered arrays, built from the padded copy on the first frame that needs them -------------------
+cudaError_t make_point_texture(cudaArray_t arr, cudaTextureObject_t* tex)
+{
+    cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    return cudaCreateTextureObject(tex, &rd, &td, nullptr);
+}
+
+// limits of layered 2-D arrays: 32768 x 32768 x 2048 layers
+template <typename T>
+bool ensure_array_t(vr_context* c)
+{
+    const int nx = c->dim[0], ny = c->dim[1], nz = c->dim[2];
+    if (nz > 2048 || nx > 32768 || ny > 32768) return false;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(T), 0, 0, 0, cudaChannelFormatKindUnsigned);
+    cudaArray_t arr = nullptr;
+    if (cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz), cudaArrayLayered) != cudaSuccess) { cudaGetLastError(); return false; }
+    // interior of the padded copy: voxel (0,0,0) sits at padded (1,1,1); slice stride = pitch * (ny+2) rows
+    T* src = static_cast<T*>(c->d_vol) + (c->slice + c->pitch + 1);
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr(src, (size_t)c->pitch * sizeof(T), nx, ny + 2);
+    cp.dstArray = arr; cp.extent = make_cudaExtent(nx, ny, nz); cp.kind = cudaMemcpyDeviceToDevice;
+    cudaTextureObject_t tex = 0;
+    if (cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+        make_point_texture(arr, &tex) == cudaSuccess) {
+        c->d_arr = arr; c->tex = tex;
+        return true;
+    }
+    cudaFreeArray(arr);
+    cudaGetLastError();
+    return false;
+}
+
+bool ensure_array(vr_context* c)
+{
+    if (c->tex) return true;
+    if (c->arr_failed || !c->d_vol) return false;
+    const bool ok = c->bpv == 1 ? ensure_array_t<uint8_t>(c) : ensure_array_t<uint16_t>(c);
+    c->arr_failed = !ok;
+    return ok;
+}
+
+// z-pair array: Nz+1 layers of (z, z+1) words, packed from the padded copy and copied in chunks of layers
+// through a bounded (256 MiB) staging buffer
+template <typename T, typename W>
+bool ensure_zpair_array_t(vr_context* c)
+{
+    const int nx = c->dim[0], ny = c->dim[1], nz = c->dim[2];
+    if (nz + 1 > 2048 || nx > 32768 || ny > 32768) return false;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(W), 0, 0, 0, cudaChannelFormatKindUnsigned);
+    cudaArray_t arr = nullptr;
+    DevBuf stage;
+    const uint64_t per_layer = (uint64_t)nx * ny;
+    const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nz + 1, (256ull << 20) / (per_layer * sizeof(W))));
+    bool ok = cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz + 1), cudaArrayLayered) == cudaSuccess &&
+              stage.alloc(per_layer * (uint64_t)chunk * sizeof(W)) == cudaSuccess;
+    for (int l0 = 0; ok && l0 <= nz; l0 += chunk) {
+        const int nl = std::min(chunk, nz + 1 - l0);
+        vr::zpair_pack_kernel<T, W><<<c->sm_count * 16, 256, 0, c->stream>>>(static_cast<const T*>(c->d_vol), stage.as<W>(), nx, ny,
+                                                                             c->pitch, c->slice, l0, nl);
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(stage.p, (size_t)nx * sizeof(W), nx, ny);
+        cp.dstArray = arr; cp.dstPos = make_cudaPos(0, 0, l0);
+        cp.extent = make_cudaExtent(nx, ny, nl); cp.kind = cudaMemcpyDeviceToDevice;
+        ok = cudaGetLastError() == cudaSuccess && cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess;
+    }
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    cudaTextureObject_t tex = 0;
+    ok = ok && make_point_texture(arr, &tex) == cudaSuccess;
+    if (ok) { c->d_arr2 = arr; c->tex2 = tex; return true; }
+    if (arr) cudaFreeArray(arr);
+    cudaGetLastError();
+    return false;
+}
+
+bool ensure_zpair_array(vr_context* c)
+{
+    if (c->tex2) return true;
+    if (c->arr2_failed || !c->d_vol) return false;
+    const bool ok = c->bpv == 1 ? ensure_zpair_array_t<uint8_t, uint16_t>(c) : ensure_zpair_array_t<uint16_t, uint32_t>(c);
+    c->arr2_failed = !ok;
+    return ok;
+}
+
+// empty map for the window's lower bound: cell empty <=> cell max <= min_val
+int ensure_empty_map(vr_context* c, int32_t min_val)
+{
+    if (!c->d_cell_max) return fail(VR_ERR_NO_VOLUME, "no cell table");
+    if (c->empty_valid && c->empty_thresh == min_val) return VR_OK;
+    VR_CUDA(cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned long long), c->stream));
+    vr::cell_empty_kernel<<<std::max<int>(1, (int)std::min<uint64_t>((c->ncells + 255) / 256, (uint64_t)c->sm_count * 8)), 256, 0, c->stream>>>(
+        c->d_cell_max, c->ncells, (unsigned int)min_val, c->d_cell_bits, c->d_cell_count);
+    VR_CUDA(cudaGetLastError());
+    unsigned long long n = 0;
+    VR_CUDA(cudaMemcpyAsync(&n, c->d_cell_count, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaStreamSynchronize(c->stream));
+    c->empty_cells = n; c->empty_thresh = min_val; c->empty_valid = true;
+    return VR_OK;
+}
+
+// ---- per-frame plan --------------------------------------------------------------------------------------
+enum LoopShape { SHAPE_UNIT = 0, SHAPE_RECIP = 1, SHAPE_MARK = 2, SHAPE_MARK_CAP = 3 };
+
 struct LaunchPlan {
     vr::FrameConsts fc;
-    bool generic;
-    int tcdiv;
-    int local_rows;
+    int local_rows;       // rows this rank owns (compact height)
+    bool fast;            // the optimised kernels cover this frame
+    int form;             // vr::MarchForm
+    int shape;            // LoopShape
+    int win;              // vr::WinMode
+    bool skip;            // empty-space skipping form
+    bool lut_final;       // the kernel reads the host-finalised opacity LUT
+    int kernel;           // VR_KERNEL_* that will run
 };
 
 int make_plan(vr_context* c, int compact, LaunchPlan* plan)
@@ -162,383 +305,309 @@ int make_plan(vr_context* c, int compact, LaunchPlan* plan)
     vr::FrameConsts& fc = plan->fc;
     std::memset(&fc, 0, sizeof fc);
     vr::compute_frame_consts(fc, c->W, c->H, c->dim, c->voxel_size, c->cam, c->params);
-    fc.rank = c->rank; fc.world = c->world; fc.tile_rows = c->tile_rows; fc.compact = compact;
+    fc.rank = c->rank; fc.world = c->world; fc.tile_rows = c->tile_rows; fc.compact = compact; fc.row0 = 0;
     plan->local_rows = compact_rows_of(c->H, c->rank, c->world, c->tile_rows);
 
     const vr_params& p = c->params;
-    // the transfer-function LUT alone does not need the generic loop: the pipelined gather kernel has a TF form
-    const bool tf_fast = p.use_tf != 0 && c->lut_fast_ok && c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
-                         (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
-    const bool pipe_selectable = c->tex2 != 0 && p.filter == VR_FILTER_TRILINEAR &&
-                                 (p.kernel == VR_KERNEL_AUTO || p.kernel == VR_KERNEL_TEXPAIR_PIPE);
-    const bool mip_fast = p.is_mip == 1 && p.use_tf == 0 && p.view_top != 1 && p.view_bottom != 1 && pipe_selectable;   // ... a MIP form
-    const bool swizzled = p.view_top == 1 || p.view_bottom == 1;
-    const bool view_fast = swizzled && p.is_mip != 1 && p.use_tf == 0 && pipe_selectable;   // ... and view_top / view_bottom forms
-    bool generic = (p.is_mip == 1 && !mip_fast) || (p.use_tf != 0 && !(tf_fast && p.is_mip != 1 && !swizzled)) ||
-                   (swizzled && !view_fast) ||
-                   fc.opacity_correction || !(p.max_val > p.min_val);
-    if (!generic) {
+    const bool mip = p.is_mip == 1, tf = p.use_tf != 0, swizzled = p.view_top == 1 || p.view_bottom == 1;
+    const bool oc = fc.opacity_correction != 0 && !mip;       // the oracle's MIP branch has no opacity correction
+    // What the optimised kernels assume: an ordered, non-empty window whose range passes the Markstein check; range
+    // tests on float bit patterns need alpha_scale >= +0 and a finite non-negative LUT; correctly rounded tex-coord
+    // division without div.rn.  Everything else (including every mode on such a frame) takes the generic loop.
+    bool fast = p.max_val > p.min_val && p.alpha_scale >= 0.0f && !std::signbit(p.alpha_scale) && (!tf || c->lut_fast_ok);
+    if (fast) {
         bool ok = false;
         int rc = verify_divisor(c, fc.frange, &ok);
         if (rc != VR_OK) return rc;
-        if (!ok) generic = true;
+        fast = ok;
     }
     int tcdiv = fc.tc_div_mode;
-    if (tcdiv == vr::DIV_MARKSTEIN) {
-        for (int i = 0; i < 3; ++i) {
+    if (fast && tcdiv == vr::DIV_MARKSTEIN) {
+        for (int i = 0; i < 3 && fast; ++i) {
             if (vr::is_pow2_float(fc.denom[i])) continue;
             bool ok = false;
             int rc = verify_divisor(c, fc.denom[i], &ok);
             if (rc != VR_OK) return rc;
-            if (!ok) tcdiv = vr::DIV_IEEE;
+            fast = ok;
         }
     }
-    if (generic) tcdiv = vr::DIV_IEEE;
+    // opacity correction: with a transfer function the final opacity is a function of the LUT index only and is
+    // finalised on the host (vr_set_params); without one it is evaluated per sample and needs a in [0,1]
+    plan->lut_final = false;
+    if (fast && oc) {
+        if (tf) plan->lut_final = true; else fast = p.alpha_scale <= 1.0f;
+    }
+    if (fast && plan->lut_final) {
+        // lut_final[i] = 1 - (1 - lut[i]*alpha)^step_scale, double precision like the oracle (oracle/march_oracle.c:203-208)
+        float fin[256];
+        for (int i = 0; i < 256 && fast; ++i) {
+            float a = p.tf_lut[i] * p.alpha_scale;
+            fin[i] = (float)(1.0 - std::pow(1.0 - (double)a, (double)p.step_scale));
+            fast = std::isfinite(fin[i]) && fin[i] >= 0.0f && !std::signbit(fin[i]);
+        }
+        if (fast) {
+            VR_CUDA(cudaMemcpyAsync(c->d_lut + 256, fin, sizeof fin, cudaMemcpyHostToDevice, c->stream));
+            VR_CUDA(cudaStreamSynchronize(c->stream));      // `fin` is on the stack
+        }
+    }
+    if (!fast) tcdiv = vr::DIV_IEEE;
     fc.tc_div_mode = tcdiv;
-    plan->generic = generic;
-    plan->tcdiv = tcdiv;
-    return VR_OK;
-}
+    plan->fast = fast;
 
-template <typename T, bool COUNT>
-int launch_direct_t(vr_context* c, const LaunchPlan& plan, const vr::DirectArgs& args, cudaStream_t s)
-{
-    using namespace vr;
-    const dim3 block(DIRECT_BLOCK_W * DIRECT_BLOCK_H);
-    const dim3 grid((c->W + DIRECT_BLOCK_W - 1) / DIRECT_BLOCK_W,
-                    (plan.local_rows + DIRECT_BLOCK_H - 1) / DIRECT_BLOCK_H);
-    const FrameConsts& fc = plan.fc;
-    if (COUNT || plan.generic) {
-        march_direct_kernel<T, VR_FILTER_NEAREST, DIV_IEEE, true, COUNT><<<grid, block, 0, s>>>(fc, args);
-    } else if (fc.filter == VR_FILTER_NEAREST) {
-        switch (plan.tcdiv) {
-            case DIV_RECIP_EXACT: march_direct_kernel<T, VR_FILTER_NEAREST, DIV_RECIP_EXACT, false, false><<<grid, block, 0, s>>>(fc, args); break;
-            case DIV_MARKSTEIN:   march_direct_kernel<T, VR_FILTER_NEAREST, DIV_MARKSTEIN, false, false><<<grid, block, 0, s>>>(fc, args); break;
-            default:              march_direct_kernel<T, VR_FILTER_NEAREST, DIV_IEEE, false, false><<<grid, block, 0, s>>>(fc, args); break;
-        }
-    } else {
-        switch (plan.tcdiv) {
-            case DIV_RECIP_EXACT: march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, false, false><<<grid, block, 0, s>>>(fc, args); break;
-            case DIV_MARKSTEIN:   march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_MARKSTEIN, false, false><<<grid, block, 0, s>>>(fc, args); break;
-            default:              march_direct_kernel<T, VR_FILTER_TRILINEAR, DIV_IEEE, false, false><<<grid, block, 0, s>>>(fc, args); break;
-        }
-    }
-    VR_CUDA(cudaGetLastError());
-    return VR_OK;
-}
-
-int launch_direct(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s)
-{
-    vr::DirectArgs args{};
-    args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
-    args.tf_lut = c->d_lut; args.out = d_out; args.local_rows = plan.local_rows;
-    return c->bpv == 1 ? launch_direct_t<uint8_t, false>(c, plan, args, s)
-                       : launch_direct_t<uint16_t, false>(c, plan, args, s);
-}
-
-template <typename T, int WIN>
-void launch_packed_tw(const vr::FrameConsts& fc, const vr::FastArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
-{
-    using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_packed_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_packed_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_packed_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_packed_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else                      march_packed_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-}
-
-template <typename T, int WIN>
-void launch_tex_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
-{
-    using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texgather_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texgather_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texgather_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-}
-
-// loop-shape flags shared by the packed kernels
-void packed_flags(const vr_context* c, const LaunchPlan& plan, bool* unit, bool* recip, bool* nocap)
-{
-    const vr::FrameConsts& fc = plan.fc;
-    *recip = plan.tcdiv == vr::DIV_RECIP_EXACT;
-    *unit = *recip && fc.denom[0] == 1.0f && fc.denom[1] == 1.0f && fc.denom[2] == 1.0f;
+    // loop shape
+    const bool recip = tcdiv == vr::DIV_RECIP_EXACT;
+    const bool unit = recip && fc.denom[0] == 1.0f && fc.denom[1] == 1.0f && fc.denom[2] == 1.0f;
     // VolumeRenderer.cs:115 caps the loop at 10000 iterations; a ray cannot take more than
     // |box diagonal| / step + 2 = |vol_size| / step_scale + 2 samples
     const double nmax = std::sqrt((double)c->dim[0] * c->dim[0] + (double)c->dim[1] * c->dim[1] + (double)c->dim[2] * c->dim[2]) /
                         (double)fc.step_scale + 4.0;
-    *nocap = nmax < 10000.0;
-}
+    const bool nocap = nmax < 10000.0;
+    plan->form = (swizzled || (mip && tf) || plan->lut_final) ? vr::FORM_GENERAL
+               : (oc && !tf) ? vr::FORM_GENERAL_OC
+               : mip ? vr::FORM_MIP : tf ? vr::FORM_TF : vr::FORM_DVR;
+    if (plan->form >= vr::FORM_GENERAL) plan->shape = nocap ? SHAPE_MARK : SHAPE_MARK_CAP;
+    else plan->shape = !nocap ? SHAPE_MARK_CAP : unit ? SHAPE_UNIT : recip ? SHAPE_RECIP : SHAPE_MARK;
+    plan->win = (p.min_val == 0 && c->have_stats && c->stats.max_value <= p.max_val &&
+                 (plan->form == vr::FORM_DVR || plan->form == vr::FORM_TF)) ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
 
-int launch_texgather(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
-{
-    vr::TexArgs a{};
-    a.tex = c->tex; a.out = d_out; a.local_rows = plan.local_rows;
-    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
-    bool unit, recip, nocap;
-    packed_flags(c, plan, &unit, &recip, &nocap);
-    // the element type only matters for the array's channel format; uint16_t instantiation serves both
-    if (win == vr::WIN_COVERS0) launch_tex_tw<uint16_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
-    else                        launch_tex_tw<uint16_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
-    VR_CUDA(cudaGetLastError());
+    // kernel
+    int want = p.kernel;
+    if (!fast) want = VR_KERNEL_DIRECT;
+    else if (want != VR_KERNEL_DIRECT) {
+        if (fc.filter == VR_FILTER_TRILINEAR) want = ensure_zpair_array(c) ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;
+        else want = ensure_array(c) ? VR_KERNEL_NEAREST_TEX : VR_KERNEL_DIRECT;
+    }
+    plan->kernel = want;
+
+    // empty-space skipping: valid when a sample of value <= min_val contributes exactly nothing
+    plan->skip = false;
+    if (want != VR_KERNEL_DIRECT && p.empty_skip != VR_SKIP_OFF && p.min_val >= 0 && c->d_cell_max) {
+        const float a0 = !tf ? 0.0f : plan->lut_final ? 1.0f /* checked below */ : p.tf_lut[0] * p.alpha_scale;
+        bool valid = a0 == 0.0f;
+        if (tf && plan->lut_final) valid = (float)(1.0 - std::pow(1.0 - (double)(p.tf_lut[0] * p.alpha_scale), (double)p.step_scale)) == 0.0f;
+        if (valid) {
+            int rc = ensure_empty_map(c, p.min_val);
+            if (rc != VR_OK) return rc;
+            // AUTO: the per-sample cell test costs ~12 instructions; it pays once a tenth of the cells is empty
+            plan->skip = p.empty_skip == VR_SKIP_ON ? true : c->empty_cells * 10 >= c->ncells;
+        }
+    }
     return VR_OK;
 }
 
-template <int WIN>
-void launch_nearest_tex_w(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+// ---- launchers -------------------------------------------------------------------------------------------
+template <typename T, bool COUNT>
+int launch_direct_t(vr_context* c, const LaunchPlan& plan, const vr::DirectArgs& args, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_nearest_tex_kernel<DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_nearest_tex_kernel<DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else                      march_nearest_tex_kernel<DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-}
-
-// nearest filter: integer-coordinate texel loads from the source-type layered array, software pipelined
-int launch_nearest_tex(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
-{
-    vr::TexArgs a{};
-    a.tex = c->tex; a.out = d_out; a.local_rows = plan.local_rows;
-    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
-    bool unit, recip, nocap;
-    packed_flags(c, plan, &unit, &recip, &nocap);
-    if (win == vr::WIN_COVERS0) launch_nearest_tex_w<vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
-    else                        launch_nearest_tex_w<vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+    const dim3 block(DIRECT_BLOCK_W * DIRECT_BLOCK_H);
+    // generic loop: run-time filter / MIP / TF / view swizzle / opacity correction, IEEE divisions
+    march_direct_kernel<T, VR_FILTER_NEAREST, DIV_IEEE, true, COUNT><<<grid, block, 0, s>>>(plan.fc, args);
     VR_CUDA(cudaGetLastError());
+    (void)c;
     return VR_OK;
 }
 
-template <typename T, int WIN>
-void launch_texpair_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+template <typename T, int FORM, bool SKIP>
+void launch_texpair_form(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, true, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair_kernel<T, DIV_RECIP_EXACT, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair_kernel<T, DIV_MARKSTEIN, WIN, false, true><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair_kernel<T, DIV_MARKSTEIN, WIN, false, false><<<grid, block, 0, s>>>(fc, a);
-}
-
-int launch_texpair(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
-{
-    vr::TexArgs a{};
-    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
-    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
-    bool unit, recip, nocap;
-    packed_flags(c, plan, &unit, &recip, &nocap);
-    if (c->bpv == 2) {
-        if (win == vr::WIN_COVERS0) launch_texpair_tw<uint16_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_tw<uint16_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_TP_SKIP_DEPTH : VR_TP_DEPTH, SKIP, SKIP ? VR_TP_SKIP_MINB : VR_TP_MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+    if constexpr (FORM >= FORM_GENERAL) {
+        if (plan.shape == SHAPE_MARK) VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); else VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false);
     } else {
-        if (win == vr::WIN_COVERS0) launch_texpair_tw<uint8_t, vr::WIN_COVERS0>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_tw<uint8_t, vr::WIN_CLAMP>(plan.fc, a, grid, s, unit, recip, nocap);
+        if constexpr (FORM == FORM_DVR || FORM == FORM_TF) {
+            if (plan.win == WIN_COVERS0) {
+                switch (plan.shape) {
+                    case SHAPE_UNIT:  VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return;
+                    case SHAPE_RECIP: VR_K(DIV_RECIP_EXACT, WIN_COVERS0, false, true); return;
+                    case SHAPE_MARK:  VR_K(DIV_MARKSTEIN, WIN_COVERS0, false, true); return;
+                    default:          VR_K(DIV_MARKSTEIN, WIN_COVERS0, false, false); return;
+                }
+            }
+        }
+        switch (plan.shape) {
+            case SHAPE_UNIT:  VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return;
+            case SHAPE_RECIP: VR_K(DIV_RECIP_EXACT, WIN_CLAMP, false, true); return;
+            case SHAPE_MARK:  VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return;
+            default:          VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false); return;
+        }
     }
-    VR_CUDA(cudaGetLastError());
-    return VR_OK;
+#undef VR_K
 }
 
-template <typename T, int WIN, int MINB>
-void launch_texpair2_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
+template <int FORM, bool SKIP>
+void launch_nearest_form(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, true, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair2_kernel<T, DIV_RECIP_EXACT, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, true, MINB><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair2_kernel<T, DIV_MARKSTEIN, WIN, false, false, MINB><<<grid, block, 0, s>>>(fc, a);
-}
-
-template <typename T, int WIN, int FA, int FB, int MODE>
-void launch_texpair_pipe_tw(const vr::FrameConsts& fc, const vr::TexArgs& a, dim3 grid, cudaStream_t s, bool unit, bool recip, bool nocap)
-{
-    using namespace vr;
-    const dim3 block(256);
-    if (unit && nocap)        march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, true, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
-    else if (recip && nocap)  march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
-    else if (recip)           march_texpair_pipe_kernel<T, DIV_RECIP_EXACT, WIN, false, false, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
-    else if (nocap)           march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, true, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
-    else                      march_texpair_pipe_kernel<T, DIV_MARKSTEIN, WIN, false, false, 6, FA, FB, MODE><<<grid, block, 0, s>>>(fc, a);
-}
-
-template <int FA, int FB, int MODE>
-int launch_texpair_pipe_f(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
-{
-    vr::TexArgs a{};
-    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
-    a.zlin = c->d_zlin; a.zpitch = (int)c->zpitch; a.zslice = (int)c->zslice;
-    a.tf_lut = c->d_lut;
-    const dim3 grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
-    bool unit, recip, nocap;
-    packed_flags(c, plan, &unit, &recip, &nocap);
-    if (c->bpv == 2) {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint16_t, vr::WIN_COVERS0, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint16_t, vr::WIN_CLAMP, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_nearest_kernel<TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_NN_SKIP_DEPTH : VR_NN_DEPTH, SKIP, SKIP ? VR_NN_SKIP_MINB : (FORM >= vr::FORM_GENERAL ? 5 : ((NOCAP) ? VR_NN_MINB : 6))><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+    if constexpr (FORM >= FORM_GENERAL) {
+        if (plan.shape == SHAPE_MARK) VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); else VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false);
     } else {
-        if (win == vr::WIN_COVERS0) launch_texpair_pipe_tw<uint8_t, vr::WIN_COVERS0, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
-        else                        launch_texpair_pipe_tw<uint8_t, vr::WIN_CLAMP, FA, FB, MODE>(plan.fc, a, grid, s, unit, recip, nocap);
+        if constexpr (FORM == FORM_DVR || FORM == FORM_TF) {
+            if (plan.win == WIN_COVERS0) {
+                switch (plan.shape) {
+                    case SHAPE_UNIT:  VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return;
+                    case SHAPE_RECIP: VR_K(DIV_RECIP_EXACT, WIN_COVERS0, false, true); return;
+                    case SHAPE_MARK:  VR_K(DIV_MARKSTEIN, WIN_COVERS0, false, true); return;
+                    default:          VR_K(DIV_MARKSTEIN, WIN_COVERS0, false, false); return;
+                }
+            }
+        }
+        switch (plan.shape) {
+            case SHAPE_UNIT:  VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return;
+            case SHAPE_RECIP: VR_K(DIV_RECIP_EXACT, WIN_CLAMP, false, true); return;
+            case SHAPE_MARK:  VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return;
+            default:          VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false); return;
+        }
     }
-    VR_CUDA(cudaGetLastError());
-    return VR_OK;
+#undef VR_K
 }
 
-// software-pipelined z-pair march (two fetches in flight per warp): texture gathers only, texture gather /
-// LSU alternating (hybrid), or LSU only
-int launch_texpair_pipe(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win, int kernel)
+template <typename T, bool SKIP>
+void launch_texpair_ts(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
-    if (kernel == VR_KERNEL_HYBRID) return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
-    if (kernel == VR_KERNEL_ZLSU)   return launch_texpair_pipe_f<vr::FETCH_LSU, vr::FETCH_LSU, vr::MODE_DVR>(c, plan, d_out, s, win);
-    if (plan.fc.view_top)           return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR_TOP>(c, plan, d_out, s, win);
-    if (plan.fc.view_bottom)        return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR_BOTTOM>(c, plan, d_out, s, win);
-    if (plan.fc.is_mip)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_MIP>(c, plan, d_out, s, win);
-    if (plan.fc.use_tf)             return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_TF>(c, plan, d_out, s, win);
-    return launch_texpair_pipe_f<vr::FETCH_TEX, vr::FETCH_TEX, vr::MODE_DVR>(c, plan, d_out, s, win);
+    switch (plan.form) {
+        case vr::FORM_DVR:        launch_texpair_form<T, vr::FORM_DVR, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_TF:         launch_texpair_form<T, vr::FORM_TF, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_MIP:        launch_texpair_form<T, vr::FORM_MIP, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_GENERAL:    launch_texpair_form<T, vr::FORM_GENERAL, SKIP>(plan, a, grid, s); break;
+        default:                  launch_texpair_form<T, vr::FORM_GENERAL_OC, SKIP>(plan, a, grid, s); break;
+    }
 }
 
-// two rays per thread: CTA = 64 x 8 pixels.  VR_TEXPAIR2_MINB=4 (lab) trades occupancy for registers.
-int launch_texpair2(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+template <bool SKIP>
+void launch_nearest_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
-    vr::TexArgs a{};
-    a.tex = c->tex2; a.out = d_out; a.local_rows = plan.local_rows;
-    const dim3 grid((c->W + 63) / 64, (plan.local_rows + 7) / 8);
-    bool unit, recip, nocap;
-    packed_flags(c, plan, &unit, &recip, &nocap);
-    static const int minb = [] { const char* e = std::getenv("VR_TEXPAIR2_MINB"); return e ? std::atoi(e) : 5; }();
-#define VR_TP2(T, WIN) do { if (minb == 4) launch_texpair2_tw<T, WIN, 4>(plan.fc, a, grid, s, unit, recip, nocap); \
-                            else           launch_texpair2_tw<T, WIN, 5>(plan.fc, a, grid, s, unit, recip, nocap); } while (0)
-    if (c->bpv == 2) { if (win == vr::WIN_COVERS0) VR_TP2(uint16_t, vr::WIN_COVERS0); else VR_TP2(uint16_t, vr::WIN_CLAMP); }
-    else             { if (win == vr::WIN_COVERS0) VR_TP2(uint8_t, vr::WIN_COVERS0);  else VR_TP2(uint8_t, vr::WIN_CLAMP); }
-#undef VR_TP2
-    VR_CUDA(cudaGetLastError());
-    return VR_OK;
+    switch (plan.form) {
+        case vr::FORM_DVR:        launch_nearest_form<vr::FORM_DVR, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_TF:         launch_nearest_form<vr::FORM_TF, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_MIP:        launch_nearest_form<vr::FORM_MIP, SKIP>(plan, a, grid, s); break;
+        case vr::FORM_GENERAL:    launch_nearest_form<vr::FORM_GENERAL, SKIP>(plan, a, grid, s); break;
+        default:                  launch_nearest_form<vr::FORM_GENERAL_OC, SKIP>(plan, a, grid, s); break;
+    }
 }
 
-template <typename T>
-int launch_fast_t(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, int win)
+#ifdef VR_LAB
+// development builds only (tools/lab/build_lab.sh): pipeline depth / occupancy variants of the DVR form, chosen per
+// launch through the environment: VR_LAB_TP="depth,minb"; returns -1 when the frame / variant is not covered
+template <typename T, int DEPTH, int MINB, bool SKIP>
+int lab_tp(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-    FastArgs a{};
-    a.vol = c->d_vol; a.pitch = c->pitch; a.slice_lo = (uint32_t)c->slice; a.out = d_out; a.local_rows = plan.local_rows;
-    const dim3 block(FAST_THREADS), grid((c->W + 31) / 32, (plan.local_rows + 7) / 8);
-    const FrameConsts& fc = plan.fc;
-    const bool tri = fc.filter == VR_FILTER_TRILINEAR, recip = plan.tcdiv == DIV_RECIP_EXACT, cov = win == WIN_COVERS0;
-    const uint64_t padded_voxels = c->slice * (uint64_t)(c->dim[2] + 2);
-    if (tri && padded_voxels < (1ull << 31)) {
-        // trilinear: one ray per thread, f32x2 packing inside the ray (signed 32-bit texel indices)
-        bool unit, recip2, nocap;
-        packed_flags(c, plan, &unit, &recip2, &nocap);
-        if (cov) launch_packed_tw<T, WIN_COVERS0>(fc, a, grid, s, unit, recip, nocap);
-        else     launch_packed_tw<T, WIN_CLAMP>(fc, a, grid, s, unit, recip, nocap);
-        VR_CUDA(cudaGetLastError());
-        return VR_OK;
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
+    if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
+#undef VR_K
+    return -1;
+}
+template <typename T, bool SKIP>
+int lab_tp_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int depth, int minb)
+{
+    const int key = depth * 10 + minb;
+    switch (key) {
+        case 26: return lab_tp<T, 2, 6, SKIP>(plan, a, grid, s);
+        case 25: return lab_tp<T, 2, 5, SKIP>(plan, a, grid, s);
+        case 24: return lab_tp<T, 2, 4, SKIP>(plan, a, grid, s);
+        case 36: return lab_tp<T, 3, 6, SKIP>(plan, a, grid, s);
+        case 35: return lab_tp<T, 3, 5, SKIP>(plan, a, grid, s);
+        case 34: return lab_tp<T, 3, 4, SKIP>(plan, a, grid, s);
+        case 45: return lab_tp<T, 4, 5, SKIP>(plan, a, grid, s);
+        case 44: return lab_tp<T, 4, 4, SKIP>(plan, a, grid, s);
+        default: return -1;
     }
-#define VR_FAST(F, D, W) march_fast_kernel<T, F, D, W, FLOOR_XU1, 1><<<grid, block, 0, s>>>(fc, a)
-    if (tri) {
-        if (recip) { if (cov) VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_COVERS0); else VR_FAST(VR_FILTER_TRILINEAR, DIV_RECIP_EXACT, WIN_CLAMP); }
-        else       { if (cov) VR_FAST(VR_FILTER_TRILINEAR, DIV_MARKSTEIN, WIN_COVERS0);   else VR_FAST(VR_FILTER_TRILINEAR, DIV_MARKSTEIN, WIN_CLAMP); }
+}
+template <int DEPTH, int MINB, bool SKIP>
+int lab_nn(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
+{
+    using namespace vr;
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_nearest_kernel<TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
+    if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
+#undef VR_K
+    return -1;
+}
+template <bool SKIP>
+int lab_nn_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int depth, int minb)
+{
+    switch (depth * 10 + minb) {
+        case 28: return lab_nn<2, 8, SKIP>(plan, a, grid, s);
+        case 26: return lab_nn<2, 6, SKIP>(plan, a, grid, s);
+        case 25: return lab_nn<2, 5, SKIP>(plan, a, grid, s);
+        case 24: return lab_nn<2, 4, SKIP>(plan, a, grid, s);
+        case 38: return lab_nn<3, 8, SKIP>(plan, a, grid, s);
+        case 36: return lab_nn<3, 6, SKIP>(plan, a, grid, s);
+        case 35: return lab_nn<3, 5, SKIP>(plan, a, grid, s);
+        case 46: return lab_nn<4, 6, SKIP>(plan, a, grid, s);
+        default: return -1;
+    }
+}
+int lab_launch_nearest(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
+{
+    const char* e = std::getenv("VR_LAB_NN");
+    int depth = 0, minb = 0;
+    if (!e || std::sscanf(e, "%d,%d", &depth, &minb) != 2 || plan.form != vr::FORM_DVR) return -1;
+    return plan.skip ? lab_nn_s<true>(plan, a, grid, s, depth, minb) : lab_nn_s<false>(plan, a, grid, s, depth, minb);
+}
+int lab_launch_texpair(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int bpv)
+{
+    const char* e = std::getenv("VR_LAB_TP");
+    int depth = 0, minb = 0;
+    if (!e || std::sscanf(e, "%d,%d", &depth, &minb) != 2 || plan.form != vr::FORM_DVR) return -1;
+    if (bpv == 2) return plan.skip ? lab_tp_s<uint16_t, true>(plan, a, grid, s, depth, minb) : lab_tp_s<uint16_t, false>(plan, a, grid, s, depth, minb);
+    return plan.skip ? lab_tp_s<uint8_t, true>(plan, a, grid, s, depth, minb) : lab_tp_s<uint8_t, false>(plan, a, grid, s, depth, minb);
+}
+#endif
+
+// the march.  `row0`/`row_end` select a band of this rank's local rows (compact row space); `peer_arrive` != null
+// fuses the hand-off signal into the kernel epilogue (returns *signalled = false when the kernel that ran cannot)
+int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int row_end, cudaStream_t s,
+                 unsigned int* peer_arrive, bool* signalled)
+{
+    if (signalled) *signalled = false;
+    if (row_end <= row0) return VR_OK;                      // this rank owns no row of the band (tiles < world)
+    plan.fc.row0 = row0;
+    const dim3 grid((c->W + 31) / 32, (row_end - row0 + 7) / 8);
+    if (plan.kernel == VR_KERNEL_DIRECT) {
+        vr::DirectArgs args{};
+        args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
+        args.tf_lut = c->d_lut; args.out = d_out; args.local_rows = row_end;
+        return c->bpv == 1 ? launch_direct_t<uint8_t, false>(c, plan, args, grid, s)
+                           : launch_direct_t<uint16_t, false>(c, plan, args, grid, s);
+    }
+    vr::MarchArgs a{};
+    a.out = d_out; a.local_rows = row_end;
+    a.tf_lut = plan.lut_final ? c->d_lut + 256 : c->d_lut;
+    a.lut_final = plan.lut_final ? 1 : 0;
+    a.cell_bits = c->d_cell_bits; a.cell_words = (int)((c->ncells + 31) / 32); a.cell_shift = c->cell_shift;
+    a.cell_nx = c->cells[0]; a.cell_nxy = c->cells[0] * c->cells[1];
+    a.done_counter = c->d_done; a.peer_arrive = peer_arrive; a.grid_ctas = grid.x * grid.y;
+    if (signalled) *signalled = peer_arrive != nullptr;
+    if (plan.kernel == VR_KERNEL_TEXPAIR_PIPE) {
+        a.tex = c->tex2;
+#ifdef VR_LAB
+        if (lab_launch_texpair(plan, a, grid, s, c->bpv) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
+#endif
+        if (c->bpv == 2) { if (plan.skip) launch_texpair_ts<uint16_t, true>(plan, a, grid, s); else launch_texpair_ts<uint16_t, false>(plan, a, grid, s); }
+        else             { if (plan.skip) launch_texpair_ts<uint8_t, true>(plan, a, grid, s);  else launch_texpair_ts<uint8_t, false>(plan, a, grid, s); }
     } else {
-        if (recip) { if (cov) VR_FAST(VR_FILTER_NEAREST, DIV_RECIP_EXACT, WIN_COVERS0); else VR_FAST(VR_FILTER_NEAREST, DIV_RECIP_EXACT, WIN_CLAMP); }
-        else       { if (cov) VR_FAST(VR_FILTER_NEAREST, DIV_MARKSTEIN, WIN_COVERS0);   else VR_FAST(VR_FILTER_NEAREST, DIV_MARKSTEIN, WIN_CLAMP); }
+        a.tex = c->tex;
+#ifdef VR_LAB
+        if (lab_launch_nearest(plan, a, grid, s) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
+#endif
+        if (plan.skip) launch_nearest_s<true>(plan, a, grid, s); else launch_nearest_s<false>(plan, a, grid, s);
     }
-#undef VR_FAST
     VR_CUDA(cudaGetLastError());
     return VR_OK;
 }
 
-// Linear copy of the z-pair words for the HYBRID / ZLSU lab kernels, built from the padded volume on
-// first use: word (jx, jy, L) = padded(jx, jy, L) | padded(jx, jy, L+1) << bits, same row pitch.
-template <typename T>
-bool ensure_zlin_t(vr_context* c)
+void fill_stats(vr_render_stats* stats, float ms, uint32_t launches, const LaunchPlan& plan)
 {
-    typedef typename vr::PairWord<T>::type W;
-    const uint64_t zslice = c->slice, zwords = zslice * (uint64_t)(c->dim[2] + 1);
-    if (zwords + zslice >= (1ull << 31)) return false;              // 32-bit word indices in the kernel
-    void* d_z = nullptr;
-    if (cudaMalloc(&d_z, zwords * sizeof(W) + 256) != cudaSuccess) { cudaGetLastError(); return false; }
-    vr::zpair_from_padded_kernel<T, W><<<c->sm_count * 16, 256, 0, c->stream>>>((const T*)c->d_vol, (W*)d_z, zslice, zwords);
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(d_z); cudaGetLastError(); return false; }
-    c->d_zlin = d_z; c->zpitch = c->pitch; c->zslice = zslice;
-    return true;
-}
-
-bool ensure_zlin(vr_context* c)
-{
-    if (c->d_zlin) return true;
-    if (!c->d_vol || !c->tex2) return false;
-    return c->bpv == 1 ? ensure_zlin_t<uint8_t>(c) : ensure_zlin_t<uint16_t>(c);
-}
-
-// the march: returns which kernel ran
-int launch_march(vr_context* c, const LaunchPlan& plan, float* d_out, cudaStream_t s, uint32_t* used,
-                 uint32_t* launches)
-{
-    const vr::FrameConsts& fc = plan.fc;
-    const uint64_t padded_voxels = c->slice * (uint64_t)(c->dim[2] + 2);
-    // the optimised kernels cover: DVR, default view, no TF, ordered window with a verified
-    // Markstein divisor, alpha_scale >= 0 (range tests on bit patterns), 32-bit texel indices,
-    // correctly rounded tex-coord division without div.rn
-    const bool base_ok = !plan.generic && plan.tcdiv != vr::DIV_IEEE && c->params.alpha_scale >= 0.0f;
-    const bool fast_ok = base_ok && padded_voxels < (1ull << 32);          // LSU kernels: 32-bit texel indices
-    const bool windowed_ok = fast_ok && vr::windowed_supported(fc, c->bpv, padded_voxels);
-    const int win = (c->params.min_val == 0 && c->have_stats && c->stats.max_value <= c->params.max_val)
-                        ? vr::WIN_COVERS0 : vr::WIN_CLAMP;
-    const bool tex_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex != 0;   // hardware addressing: no index limit
-    const bool texpair_ok = base_ok && fc.filter == VR_FILTER_TRILINEAR && c->tex2 != 0;
-    const bool nearest_tex_ok = base_ok && fc.filter == VR_FILTER_NEAREST && c->tex != 0;
-    int want = c->params.kernel;
-    if (want == VR_KERNEL_NEAREST_TEX && !nearest_tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
-    if (want == VR_KERNEL_AUTO && nearest_tex_ok) want = VR_KERNEL_NEAREST_TEX;
-    if ((fc.use_tf || fc.is_mip || fc.view_top || fc.view_bottom) && !plan.generic) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : VR_KERNEL_DIRECT;   // make_plan guarantees AUTO / TEXPAIR_PIPE here
-    if (want == VR_KERNEL_AUTO) want = texpair_ok ? VR_KERNEL_TEXPAIR_PIPE : tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
-    const bool zlin_ok = texpair_ok && (c->params.kernel == VR_KERNEL_HYBRID || c->params.kernel == VR_KERNEL_ZLSU) && ensure_zlin(c);
-    if ((want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) && !zlin_ok) want = VR_KERNEL_TEXPAIR_PIPE;
-    if ((want == VR_KERNEL_TEXPAIR2 || want == VR_KERNEL_TEXPAIR_PIPE) && !texpair_ok) want = VR_KERNEL_TEXPAIR;
-    if (want == VR_KERNEL_TEXPAIR && !texpair_ok) want = tex_ok ? VR_KERNEL_TEXGATHER : (fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT);
-    if (want == VR_KERNEL_TEXGATHER && !tex_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
-    if (want == VR_KERNEL_WINDOWED && !windowed_ok) want = fast_ok ? VR_KERNEL_FAST : VR_KERNEL_DIRECT;
-    if (want == VR_KERNEL_FAST && !fast_ok) want = VR_KERNEL_DIRECT;
-    *launches = 1;
-    if (want == VR_KERNEL_WINDOWED) {
-        int rc = c->bpv == 1
-            ? vr::launch_windowed_t<uint8_t>(c->win, fc, c->d_vol, c->pitch, c->slice, c->dim[1], c->dim[2], d_out, plan.local_rows, c->sm_count, plan.tcdiv, win, s, false)
-            : vr::launch_windowed_t<uint16_t>(c->win, fc, c->d_vol, c->pitch, c->slice, c->dim[1], c->dim[2], d_out, plan.local_rows, c->sm_count, plan.tcdiv, win, s, false);
-        if (rc == 0) { *used = VR_KERNEL_WINDOWED; return VR_OK; }
-        // no tensor map for this volume (e.g. smaller than one TMA box): use the L1 path
-        cudaGetLastError();
-        want = VR_KERNEL_FAST;
-    }
-    if (want == VR_KERNEL_NEAREST_TEX) {
-        *used = VR_KERNEL_NEAREST_TEX;
-        return launch_nearest_tex(c, plan, d_out, s, win);
-    }
-    if (want == VR_KERNEL_TEXPAIR_PIPE || want == VR_KERNEL_HYBRID || want == VR_KERNEL_ZLSU) {
-        *used = (uint32_t)want;
-        return launch_texpair_pipe(c, plan, d_out, s, win, want);
-    }
-    if (want == VR_KERNEL_TEXPAIR2) {
-        *used = VR_KERNEL_TEXPAIR2;
-        return launch_texpair2(c, plan, d_out, s, win);
-    }
-    if (want == VR_KERNEL_TEXPAIR) {
-        *used = VR_KERNEL_TEXPAIR;
-        return launch_texpair(c, plan, d_out, s, win);
-    }
-    if (want == VR_KERNEL_TEXGATHER) {
-        *used = VR_KERNEL_TEXGATHER;
-        return launch_texgather(c, plan, d_out, s, win);
-    }
-    if (want == VR_KERNEL_FAST) {
-        *used = VR_KERNEL_FAST;
-        return c->bpv == 1 ? launch_fast_t<uint8_t>(c, plan, d_out, s, win) : launch_fast_t<uint16_t>(c, plan, d_out, s, win);
-    }
-    *used = VR_KERNEL_DIRECT;
-    return launch_direct(c, plan, d_out, s);
+    if (!stats) return;
+    stats->kernel_ms = ms; stats->kernel_launches = launches; stats->kernel_used = (uint32_t)plan.kernel;
+    stats->skip_used = plan.skip ? 1u : 0u;
 }
 
 int render_common(vr_context* c, float* d_out, int compact, cudaStream_t s, vr_render_stats* stats)
@@ -546,147 +615,115 @@ int render_common(vr_context* c, float* d_out, int compact, cudaStream_t s, vr_r
     LaunchPlan plan;
     int rc = make_plan(c, compact, &plan);
     if (rc != VR_OK) return rc;
-    uint32_t used = 0, launches = 0;
     VR_CUDA(cudaEventRecord(c->ev0, s));
-    rc = launch_march(c, plan, d_out, s, &used, &launches);
+    rc = launch_march(c, plan, d_out, 0, plan.local_rows, s, nullptr, nullptr);
     if (rc != VR_OK) return rc;
     VR_CUDA(cudaEventRecord(c->ev1, s));
     VR_CUDA(cudaEventSynchronize(c->ev1));
     float ms = 0.f;
     VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    if (stats) { stats->kernel_ms = ms; stats->kernel_launches = launches; stats->kernel_used = used; }
+    fill_stats(stats, ms, plan.local_rows > 0 ? 1u : 0u, plan);
     return VR_OK;
 }
 
+void release_volume(vr_context* c)
+{
+    if (c->tex) { cudaDestroyTextureObject(c->tex); c->tex = 0; }
+    if (c->d_arr) { cudaFreeArray(c->d_arr); c->d_arr = nullptr; }
+    if (c->tex2) { cudaDestroyTextureObject(c->tex2); c->tex2 = 0; }
+    if (c->d_arr2) { cudaFreeArray(c->d_arr2); c->d_arr2 = nullptr; }
+    if (c->d_vol) { cudaFree(c->d_vol); c->d_vol = nullptr; }
+    if (c->d_cell_min) { cudaFree(c->d_cell_min); c->d_cell_min = nullptr; }
+    if (c->d_cell_max) { cudaFree(c->d_cell_max); c->d_cell_max = nullptr; }
+    if (c->d_cell_bits) { cudaFree(c->d_cell_bits); c->d_cell_bits = nullptr; }
+    c->arr_failed = c->arr2_failed = false;
+    c->empty_valid = false; c->ncells = 0; c->vol_bytes = 0;
+    c->have_stats = false;
+}
+
+// Volume ingest from a device-resident x-fastest source (RendererCore.cpp:360-419 on the GPU):
+//   pass 1  pad_minmax_kernel   ONE read of the source: edge-replicated linear copy + min/max
+//   pass 2  histogram_kernel    (needs the max of pass 1 for the 16-bit binning, RendererCore.cpp:386-398)
+//   pass 3  cell_minmax_kernel  per-cell min/max table (reads the padded copy ~1.1x)
+// The layered arrays are built later, from the padded copy, by the first frame that needs them.  Everything is
+// allocated into locals first; the context is only touched once nothing can fail any more.
+// Peak footprint during the call: source + padded copy (+ the previous volume until the swap).
 template <typename T>
 int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
 {
     const int nx = (int)dims[0], ny = (int)dims[1], nz = (int)dims[2];
     const uint64_t n = (uint64_t)nx * ny * nz;
-    // stats first (RendererCore.cpp:360-405)
-    unsigned int* d_mm = nullptr;
-    unsigned long long* d_bins = nullptr;
-    VR_CUDA(cudaMalloc(&d_mm, 2 * sizeof(unsigned int)));
-    VR_CUDA(cudaMalloc(&d_bins, 256 * sizeof(unsigned long long)));
+    DevBuf mm, bins, hlut, padded, cmin, cmax, cempty;
+    VR_CUDA(mm.alloc(2 * sizeof(unsigned int)));
+    VR_CUDA(bins.alloc(256 * sizeof(unsigned long long)));
     const unsigned int init[2] = {0xffffffffu, 0u};
-    VR_CUDA(cudaMemcpyAsync(d_mm, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
-    VR_CUDA(cudaMemsetAsync(d_bins, 0, 256 * sizeof(unsigned long long), c->stream));
-    const int blocks = c->sm_count * 8;
-    unsigned int mm[2] = {0, 255};
-    if (sizeof(T) == 2) {
-        vr::minmax_kernel<T><<<blocks, 256, 0, c->stream>>>(d_src, n, d_mm, d_mm + 1);
-        VR_CUDA(cudaGetLastError());
-        VR_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
-        VR_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    {
-        uint8_t* d_hlut = nullptr;
-        size_t smem = (vr::HIST_THREADS / 32) * 256 * sizeof(unsigned int);
-        if (sizeof(T) == 2) {
-            VR_CUDA(cudaMalloc(&d_hlut, 65536));
-            vr::histogram_lut_kernel<<<65536 / 256, 256, 0, c->stream>>>((float)(int)mm[1], d_hlut);
-            smem += 65536;
-            VR_CUDA(cudaFuncSetAttribute(vr::histogram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        vr::histogram_kernel<T><<<c->sm_count * 3, vr::HIST_THREADS, smem, c->stream>>>(d_src, n, d_hlut, d_bins);
-        cudaError_t he = cudaGetLastError();
-        if (he == cudaSuccess) he = cudaStreamSynchronize(c->stream);
-        if (d_hlut) cudaFree(d_hlut);
-        if (he != cudaSuccess) { cudaFree(d_mm); cudaFree(d_bins); return cuda_fail(he, "histogram_kernel"); }
-    }
-    unsigned long long bins[256];
-    VR_CUDA(cudaMemcpyAsync(bins, d_bins, sizeof bins, cudaMemcpyDeviceToHost, c->stream));
+    VR_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    VR_CUDA(cudaMemsetAsync(bins.p, 0, 256 * sizeof(unsigned long long), c->stream));
 
-    // padded copy
+    // pass 1: padded copy + min/max
     const uint32_t pitch = (uint32_t)(round_up((uint64_t)(nx + 2) * sizeof(T), 16) / sizeof(T));
     const uint64_t slice = (uint64_t)pitch * (uint64_t)(ny + 2);
     const uint64_t bytes = slice * (uint64_t)(nz + 2) * sizeof(T) + 256;
-    void* d_new = nullptr;
-    cudaError_t e = cudaMalloc(&d_new, bytes);
-    if (e != cudaSuccess) { cudaFree(d_mm); cudaFree(d_bins); return cuda_fail(e, "cudaMalloc(padded volume)"); }
-    VR_CUDA(cudaMemsetAsync(d_new, 0, bytes, c->stream));
-    vr::pad_volume_kernel<T><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, (T*)d_new, nx, ny, nz, pitch);
+    VR_CUDA(padded.alloc(bytes));
+    VR_CUDA(cudaMemsetAsync(static_cast<char*>(padded.p) + bytes - 256, 0, 256, c->stream));
+    vr::pad_minmax_kernel<T><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, padded.as<T>(), nx, ny, nz, pitch,
+                                                                      mm.as<unsigned int>(), mm.as<unsigned int>() + 1);
     VR_CUDA(cudaGetLastError());
+    unsigned int mmh[2] = {0, 255};
+    VR_CUDA(cudaMemcpyAsync(mmh, mm.p, sizeof mmh, cudaMemcpyDeviceToHost, c->stream));
     VR_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_mm); cudaFree(d_bins);
 
-    // layered array for the gather kernel (limits of layered 2-D arrays: 32768 x 32768 x 2048)
-    if (c->tex) { cudaDestroyTextureObject(c->tex); c->tex = 0; }
-    if (c->d_arr) { cudaFreeArray(c->d_arr); c->d_arr = nullptr; }
-    if (nz <= 2048 && nx <= 32768 && ny <= 32768) {
-        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(T), 0, 0, 0, cudaChannelFormatKindUnsigned);
-        cudaArray_t arr = nullptr;
-        if (cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz), cudaArrayLayered) == cudaSuccess) {
-            cudaMemcpy3DParms cp = {};
-            cp.srcPtr = make_cudaPitchedPtr(const_cast<T*>(d_src), (size_t)nx * sizeof(T), nx, ny);
-            cp.dstArray = arr; cp.extent = make_cudaExtent(nx, ny, nz); cp.kind = cudaMemcpyDeviceToDevice;
-            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
-            cudaTextureDesc td = {};
-            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-            cudaTextureObject_t tex = 0;
-            if (cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess &&
-                cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess) {
-                c->d_arr = arr; c->tex = tex;
-            } else {
-                cudaFreeArray(arr);
-            }
+    // pass 2: histogram
+    {
+        size_t smem = (vr::HIST_THREADS / 32) * 256 * sizeof(unsigned int);
+        if (sizeof(T) == 2) {
+            VR_CUDA(hlut.alloc(65536));
+            vr::histogram_lut_kernel<<<65536 / 256, 256, 0, c->stream>>>((float)(int)mmh[1], hlut.as<uint8_t>());
+            smem += 65536;
+            VR_CUDA(cudaFuncSetAttribute(vr::histogram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        cudaGetLastError();     // without the array the LDG kernels serve every frame
+        vr::histogram_kernel<T><<<c->sm_count * 3, vr::HIST_THREADS, smem, c->stream>>>(d_src, n, hlut.as<uint8_t>(), bins.as<unsigned long long>());
+        VR_CUDA(cudaGetLastError());
     }
-    // z-pair array for the texpair kernel: Nz+1 layers of (z, z+1) words, packed and copied in
-    // chunks of layers through a bounded staging buffer
-    if (c->tex2) { cudaDestroyTextureObject(c->tex2); c->tex2 = 0; }
-    if (c->d_arr2) { cudaFreeArray(c->d_arr2); c->d_arr2 = nullptr; }
-    if (nz + 1 <= 2048 && nx <= 32768 && ny <= 32768) {
-        typedef typename vr::PairWord<T>::type W;
-        cudaChannelFormatDesc cd = cudaCreateChannelDesc(8 * (int)sizeof(W), 0, 0, 0, cudaChannelFormatKindUnsigned);
-        cudaArray_t arr = nullptr;
-        W* d_stage = nullptr;
-        const uint64_t per_layer = (uint64_t)nx * ny;
-        const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nz + 1, (256ull << 20) / (per_layer * sizeof(W))));
-        bool ok = cudaMalloc3DArray(&arr, &cd, make_cudaExtent(nx, ny, nz + 1), cudaArrayLayered) == cudaSuccess &&
-                  cudaMalloc(&d_stage, per_layer * (uint64_t)chunk * sizeof(W)) == cudaSuccess;
-        for (int l0 = 0; ok && l0 <= nz; l0 += chunk) {
-            const int nl = std::min(chunk, nz + 1 - l0);
-            vr::zpair_pack_kernel<T, W><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, d_stage, nx, ny, nz, l0, nl);
-            cudaMemcpy3DParms cp = {};
-            cp.srcPtr = make_cudaPitchedPtr(d_stage, (size_t)nx * sizeof(W), nx, ny);
-            cp.dstArray = arr; cp.dstPos = make_cudaPos(0, 0, l0);
-            cp.extent = make_cudaExtent(nx, ny, nl); cp.kind = cudaMemcpyDeviceToDevice;
-            ok = cudaGetLastError() == cudaSuccess && cudaMemcpy3DAsync(&cp, c->stream) == cudaSuccess;
-        }
-        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
-        if (d_stage) cudaFree(d_stage);
-        cudaTextureObject_t tex = 0;
-        if (ok) {
-            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
-            cudaTextureDesc td = {};
-            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-            ok = cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess;
-        }
-        if (ok) { c->d_arr2 = arr; c->tex2 = tex; }
-        else if (arr) cudaFreeArray(arr);
-        cudaGetLastError();     // without the array the other kernels serve every frame
-    }
-    if (c->d_zlin) { cudaFree(c->d_zlin); c->d_zlin = nullptr; }      // rebuilt on demand (ensure_zlin)
-    if (c->d_vol) cudaFree(c->d_vol);
-    c->d_vol = d_new; c->vol_bytes = bytes;
+    unsigned long long hbins[256];
+    VR_CUDA(cudaMemcpyAsync(hbins, bins.p, sizeof hbins, cudaMemcpyDeviceToHost, c->stream));
+
+    // pass 3: cell table.  Smallest cell side >= 8 voxels with at most 65536 cells: the empty map then stays
+    // resident in L1 next to the texture working set.
+    int shift = 3;
+    auto cells_of = [&](int sh, int a) { return (int)(dims[a] >> sh) + 1; };
+    while ((uint64_t)cells_of(shift, 0) * cells_of(shift, 1) * cells_of(shift, 2) > 65536ull) ++shift;
+    const int cnx = cells_of(shift, 0), cny = cells_of(shift, 1), cnz = cells_of(shift, 2);
+    const uint64_t ncells = (uint64_t)cnx * cny * cnz;
+    VR_CUDA(cmin.alloc(ncells * sizeof(uint16_t)));
+    VR_CUDA(cmax.alloc(ncells * sizeof(uint16_t)));
+    VR_CUDA(cempty.alloc(((ncells + 31) / 32) * sizeof(uint32_t)));
+    vr::cell_minmax_kernel<T><<<(unsigned)std::min<uint64_t>(ncells, (uint64_t)c->sm_count * 32), 128, 0, c->stream>>>(
+        padded.as<T>(), pitch, slice, nx, ny, nz, shift, cnx, cny, cnz, cmin.as<uint16_t>(), cmax.as<uint16_t>());
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaStreamSynchronize(c->stream));          // also completes the D2H copy into `hbins`
+
+    // nothing can fail from here: swap the new volume in
+    if (!c->d_cell_count) VR_CUDA(cudaMalloc(&c->d_cell_count, sizeof(unsigned long long)));
+    release_volume(c);
+    c->d_vol = padded.release(); c->vol_bytes = bytes;
     c->dim[0] = nx; c->dim[1] = ny; c->dim[2] = nz;
     c->bpv = (int)sizeof(T); c->pitch = pitch; c->slice = slice;
-    vr::windowed_invalidate(c->win);
+    c->d_cell_min = static_cast<uint16_t*>(cmin.release());
+    c->d_cell_max = static_cast<uint16_t*>(cmax.release());
+    c->d_cell_bits = static_cast<uint32_t*>(cempty.release());
+    c->cell_shift = shift; c->cells[0] = cnx; c->cells[1] = cny; c->cells[2] = cnz; c->ncells = ncells;
 
     // histogram normalisation exactly as RendererCore.cpp:361,386-405: float bins that are
     // incremented one by one saturate at 2^24; max_value starts at the 16-bit dataset max
     // (or -1 for 8-bit data) and is then raised by the bin counts.
     vr_volume_stats& st = c->stats;
-    if (sizeof(T) == 2) { st.min_value = (int)mm[0]; st.max_value = (int)mm[1]; }
+    if (sizeof(T) == 2) { st.min_value = (int)mmh[0]; st.max_value = (int)mmh[1]; }
     else { st.min_value = 0; st.max_value = 255; }
-    int max_value = sizeof(T) == 2 ? (int)mm[1] : -1;
+    int max_value = sizeof(T) == 2 ? (int)mmh[1] : -1;
     float hist[256];
     for (int i = 0; i < 256; ++i) {
-        const unsigned long long cnt = bins[i] > 16777216ull ? 16777216ull : bins[i];
+        const unsigned long long cnt = hbins[i] > 16777216ull ? 16777216ull : hbins[i];
         hist[i] = (float)cnt;
         if (i > 0 && hist[i] > (float)max_value) max_value = (int)hist[i];
     }
@@ -724,6 +761,7 @@ void vr_params_default(vr_params* p)
     p->filter = VR_FILTER_NEAREST;
     p->step_scale = 1.0f;
     p->kernel = VR_KERNEL_AUTO;
+    p->empty_skip = VR_SKIP_AUTO;
 }
 
 int vr_device_count(int* count)
@@ -755,9 +793,13 @@ int vr_create(int device, int width, int height, vr_context** out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_frame, frame_alloc_bytes(width, height));
     if (e == cudaSuccess) e = cudaMemset(c->d_frame + (size_t)width * height * 4, 0, FRAME_SYNC_BYTES);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, 256 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, 512 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flag, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_lut, 0, 256 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->d_lut, 0, 512 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_peer_error, sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *c->h_peer_error = 0; e = cudaHostGetDevicePointer(&c->d_peer_error, c->h_peer_error, 0); }
     if (e != cudaSuccess) { int rc = cuda_fail(e, "vr_create"); vr_destroy(c); return rc; }
     *out = c;
     return VR_OK;
@@ -767,13 +809,10 @@ void vr_destroy(vr_context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    vr::windowed_release(c->win);
-    if (c->tex) cudaDestroyTextureObject(c->tex);
-    if (c->d_arr) cudaFreeArray(c->d_arr);
-    if (c->tex2) cudaDestroyTextureObject(c->tex2);
-    if (c->d_arr2) cudaFreeArray(c->d_arr2);
-    if (c->d_zlin) cudaFree(c->d_zlin);
-    if (c->d_vol) cudaFree(c->d_vol);
+    release_volume(c);
+    if (c->d_cell_count) cudaFree(c->d_cell_count);
+    if (c->d_done) cudaFree(c->d_done);
+    if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_rgb8) cudaFree(c->d_rgb8);
     if (c->d_lut) cudaFree(c->d_lut);
@@ -862,6 +901,40 @@ int vr_volume_stats_get(vr_context* c, vr_volume_stats* out)
     return VR_OK;
 }
 
+int vr_cell_table_get(vr_context* c, int* shift, int cells[3], uint16_t* mins, uint16_t* maxs, uint64_t* empty_cells)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_cell_table_get: null context");
+    if (!c->d_cell_max) return fail(VR_ERR_NO_VOLUME, "vr_cell_table_get: no volume uploaded");
+    VR_CUDA(cudaSetDevice(c->device));
+    if (shift) *shift = c->cell_shift;
+    if (cells) for (int i = 0; i < 3; ++i) cells[i] = c->cells[i];
+    if (mins) VR_CUDA(cudaMemcpy(mins, c->d_cell_min, c->ncells * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (maxs) VR_CUDA(cudaMemcpy(maxs, c->d_cell_max, c->ncells * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (empty_cells) {
+        *empty_cells = 0;
+        if (c->params.min_val >= 0) {
+            int rc = ensure_empty_map(c, c->params.min_val);
+            if (rc != VR_OK) return rc;
+            *empty_cells = c->empty_cells;
+        }
+    }
+    return VR_OK;
+}
+
+int vr_memory_info_get(vr_context* c, vr_memory_info* out)
+{
+    if (!c || !out) return fail(VR_ERR_INVALID, "vr_memory_info_get: null");
+    std::memset(out, 0, sizeof *out);
+    out->frame_bytes = frame_alloc_bytes(c->W, c->H);
+    if (!c->d_vol) return VR_OK;
+    const uint64_t nvox = (uint64_t)c->dim[0] * c->dim[1] * c->dim[2];
+    out->linear_bytes = c->vol_bytes;
+    out->array_bytes = c->d_arr ? nvox * (uint64_t)c->bpv : 0;
+    out->zpair_array_bytes = c->d_arr2 ? (uint64_t)c->dim[0] * c->dim[1] * (uint64_t)(c->dim[2] + 1) * 2ull * (uint64_t)c->bpv : 0;
+    out->cell_table_bytes = c->ncells * 4ull + ((c->ncells + 31) / 32) * 4ull;
+    return VR_OK;
+}
+
 int vr_set_camera(vr_context* c, const float cam21[21])
 {
     if (!c || !cam21) return fail(VR_ERR_INVALID, "vr_set_camera: null");
@@ -880,8 +953,10 @@ int vr_set_params(vr_context* c, const vr_params* p)
     if (!std::isfinite(p->alpha_scale)) return fail(VR_ERR_INVALID, "vr_set_params: alpha_scale not finite");
     if (!(p->step_scale > 0.0f) || !std::isfinite(p->step_scale))
         return fail(VR_ERR_INVALID, "vr_set_params: step_scale must be finite and > 0");
-    if (p->kernel < VR_KERNEL_AUTO || p->kernel > VR_KERNEL_NEAREST_TEX)
-        return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel");
+    if (p->kernel != VR_KERNEL_AUTO && p->kernel != VR_KERNEL_DIRECT && p->kernel != VR_KERNEL_TEXPAIR_PIPE && p->kernel != VR_KERNEL_NEAREST_TEX)
+        return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel (AUTO, DIRECT, TEXPAIR_PIPE, NEAREST_TEX)");
+    if (p->empty_skip < VR_SKIP_AUTO || p->empty_skip > VR_SKIP_OFF)
+        return fail(VR_ERR_INVALID, "vr_set_params: unknown empty_skip mode");
     if (p->use_tf) {
         // the optimised loop tests ranges on float bit patterns: it needs a finite, non-negative opacity LUT
         bool ok = true;
@@ -931,57 +1006,82 @@ int vr_render_device(vr_context* c, float* d_rgba, int compact, void* cuda_strea
     return VR_OK;
 }
 
-// vr_render for an unpartitioned frame: BANDS horizontal bands, each marched on its own stream and
-// followed there by the device->host copy of its rows, so only the last band's copy is exposed
-// (33 MB over PCIe cost 0.7 ms per 1080p frame when copied after the whole march).  A band is rendered
-// through the row-tile partition (rank = band, world = BANDS, one tile per band): no kernel changes.
+static int ensure_bands(vr_context* c)
+{
+    if (c->bands_ready) return VR_OK;
+    for (int b = 0; b < vr_context::BANDS; ++b) {
+        VR_CUDA(cudaStreamCreateWithFlags(&c->band_stream[b], cudaStreamNonBlocking));
+        VR_CUDA(cudaEventCreateWithFlags(&c->band_kdone[b], cudaEventDisableTiming));
+        VR_CUDA(cudaEventCreateWithFlags(&c->band_cdone[b], cudaEventDisableTiming));
+    }
+    c->bands_ready = true;
+    return VR_OK;
+}
+
+// Render this rank's rows as up to BANDS bands of whole row tiles, each marched on its own stream and followed
+// there by the device->host copy of its rows, so that only the last band's copy is exposed (33 MB over PCIe
+// cost 0.7 ms per 1080p frame when copied after the whole march).  `full_frame` = 1: unpartitioned frame, the
+// host buffer receives every row (vr_render); 0: the rank's row tiles land in their rows of a full host frame
+// that other ranks fill too (vr_render_owned_to_host).  The device image is compact (owned rows only).
 static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats)
 {
     constexpr int B = vr_context::BANDS;
-    if (!c->bands_ready) {
-        for (int b = 0; b < B; ++b) {
-            VR_CUDA(cudaStreamCreateWithFlags(&c->band_stream[b], cudaStreamNonBlocking));
-            VR_CUDA(cudaEventCreateWithFlags(&c->band_kdone[b], cudaEventDisableTiming));
-            VR_CUDA(cudaEventCreateWithFlags(&c->band_cdone[b], cudaEventDisableTiming));
-        }
-        c->bands_ready = true;
-    }
-    const int band_rows = (int)round_up((uint64_t)(c->H + B - 1) / B, 8);
-    const int save_rank = c->rank, save_world = c->world, save_tile = c->tile_rows;
-    uint32_t used = 0, launches = 0, total_launches = 0;
-    int rc = VR_OK, nb = 0;
+    int rc = ensure_bands(c);
+    if (rc != VR_OK) return rc;
+    LaunchPlan plan;
+    rc = make_plan(c, /*compact=*/1, &plan);
+    if (rc != VR_OK) return rc;
+    const int T = c->tile_rows;
+    const int local_tiles = plan.local_rows / T;
+    const int tiles_per_band = std::max(1, (local_tiles + B - 1) / B);
+    const size_t row_floats = (size_t)c->W * 4;
+    uint32_t launches = 0;
+    int nb = 0;
     cudaError_t e = cudaEventRecord(c->ev0, c->stream);
     for (int b = 0; b < B && rc == VR_OK && e == cudaSuccess; ++b) {
-        const int y0 = b * band_rows, y1 = std::min(c->H, y0 + band_rows);
-        if (y0 >= c->H) break;
-        c->rank = b; c->world = B; c->tile_rows = band_rows;
-        LaunchPlan plan;
-        rc = make_plan(c, 0, &plan);
-        if (rc != VR_OK) break;
+        const int t0 = b * tiles_per_band, t1 = std::min(local_tiles, t0 + tiles_per_band);
+        if (t0 >= t1) break;
         cudaStream_t bs = c->band_stream[b];
         e = cudaStreamWaitEvent(bs, c->ev0, 0);
-        if (e == cudaSuccess) rc = launch_march(c, plan, c->d_frame, bs, &used, &launches);
-        total_launches += launches;
+        if (e == cudaSuccess) rc = launch_march(c, plan, c->d_frame, t0 * T, t1 * T, bs, nullptr, nullptr);
+        ++launches;
         if (e == cudaSuccess) e = cudaEventRecord(c->band_kdone[b], bs);
-        const size_t off = (size_t)y0 * c->W * 4, n = (size_t)(y1 - y0) * c->W * 4 * sizeof(float);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(host_rgba + off, c->d_frame + off, n, cudaMemcpyDeviceToHost, bs);
+        for (int lt = t0; lt < t1 && e == cudaSuccess; ++lt) {
+            const int y0 = (lt * c->world + c->rank) * T, rows = std::min(T, c->H - y0);
+            // consecutive local tiles are consecutive image rows when the frame is not partitioned: one copy per band
+            if (c->world == 1) {
+                const int y1 = std::min(c->H, t1 * T);
+                e = cudaMemcpyAsync(host_rgba + (size_t)y0 * row_floats, c->d_frame + (size_t)lt * T * row_floats,
+                                    (size_t)(y1 - y0) * row_floats * sizeof(float), cudaMemcpyDeviceToHost, bs);
+                break;
+            }
+            if (rows > 0)
+                e = cudaMemcpyAsync(host_rgba + (size_t)y0 * row_floats, c->d_frame + (size_t)lt * T * row_floats,
+                                    (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, bs);
+        }
         if (e == cudaSuccess) e = cudaEventRecord(c->band_cdone[b], bs);
         nb = b + 1;
     }
-    c->rank = save_rank; c->world = save_world; c->tile_rows = save_tile;
     for (int b = 0; b < nb && e == cudaSuccess; ++b) e = cudaStreamWaitEvent(c->stream, c->band_kdone[b], 0);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);           // every band's march has finished
     for (int b = 0; b < nb && e == cudaSuccess; ++b) e = cudaStreamWaitEvent(c->stream, c->band_cdone[b], 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || rc != VR_OK) {
         for (int b = 0; b < nb; ++b) cudaStreamSynchronize(c->band_stream[b]);
-        return cuda_fail(e, "vr_render (banded)");
+        return e != cudaSuccess ? cuda_fail(e, "banded render") : rc;
     }
-    if (rc != VR_OK) { for (int b = 0; b < nb; ++b) cudaStreamSynchronize(c->band_stream[b]); return rc; }
     float ms = 0.f;
     VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    if (stats) { stats->kernel_ms = ms; stats->kernel_launches = total_launches; stats->kernel_used = used; }
+    fill_stats(stats, ms, launches, plan);
     return VR_OK;
+}
+
+static bool banding_pays(const vr_context* c)
+{
+    static const bool no_bands = std::getenv("VR_NO_BANDS") != nullptr;
+    // small frames copy in microseconds: four launches on four streams would cost more than they hide
+    const size_t owned_px = (size_t)c->W * (size_t)compact_rows_of(c->H, c->rank, c->world, c->tile_rows);
+    return !no_bands && owned_px >= ((size_t)1 << 17) && compact_rows_of(c->H, c->rank, c->world, c->tile_rows) >= 2 * c->tile_rows;
 }
 
 int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
@@ -990,21 +1090,18 @@ int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
     VR_CUDA(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     const size_t bytes = (size_t)c->W * c->H * 4 * sizeof(float);
-    // stateless kernels only (the windowed kernel keeps per-context scratch)
-    static const bool no_bands = std::getenv("VR_NO_BANDS") != nullptr;
-    // small frames copy in microseconds: four launches on four streams would cost more than they hide
-    const bool worth_banding = (size_t)c->W * c->H >= ((size_t)1 << 19);
-    if (!no_bands && worth_banding && c->world == 1 && c->H >= 8 * vr_context::BANDS && c->params.kernel != VR_KERNEL_WINDOWED) {
-        int rc = render_banded(c, host_rgba, stats);
+    int rc;
+    if (c->world == 1 && banding_pays(c)) {
+        // the banded path leaves the frame in the context's buffer too (compact == full when world == 1)
+        rc = render_banded(c, host_rgba, stats);
         if (rc != VR_OK) return rc;
-        if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        return VR_OK;
+    } else {
+        if (c->world > 1) VR_CUDA(cudaMemsetAsync(c->d_frame, 0, bytes, c->stream));
+        rc = render_common(c, c->d_frame, 0, c->stream, stats);
+        if (rc != VR_OK) return rc;
+        VR_CUDA(cudaMemcpyAsync(host_rgba, c->d_frame, bytes, cudaMemcpyDeviceToHost, c->stream));
+        VR_CUDA(cudaStreamSynchronize(c->stream));
     }
-    if (c->world > 1) VR_CUDA(cudaMemsetAsync(c->d_frame, 0, bytes, c->stream));
-    int rc = render_common(c, c->d_frame, 0, c->stream, stats);
-    if (rc != VR_OK) return rc;
-    VR_CUDA(cudaMemcpyAsync(host_rgba, c->d_frame, bytes, cudaMemcpyDeviceToHost, c->stream));
-    VR_CUDA(cudaStreamSynchronize(c->stream));
     if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return VR_OK;
 }
@@ -1012,23 +1109,30 @@ int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
 // Multi-GPU end to end: this rank's row tiles straight into a FULL host frame (one buffer shared by all
 // ranks, e.g. POSIX shared memory registered with cudaHostRegister in every process): N PCIe links carry
 // the frame instead of rank 0's one, and nothing crosses NVLink.  Rows this rank does not own are not touched.
+// Banded like vr_render: a band's tiles are copied while the following bands are still marching.
 int vr_render_owned_to_host(vr_context* c, float* host_full_frame, vr_render_stats* stats)
 {
     if (!c || !host_full_frame) return fail(VR_ERR_INVALID, "vr_render_owned_to_host: null argument");
     VR_CUDA(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
-    int rc = render_common(c, c->d_frame, /*compact=*/1, c->stream, stats);     // compact tiles fit in the frame buffer
-    if (rc != VR_OK) return rc;
-    const int tiles = (c->H + c->tile_rows - 1) / c->tile_rows;
-    const size_t row_floats = (size_t)c->W * 4;
-    int local_tile = 0;
-    for (int t = c->rank; t < tiles; t += c->world, ++local_tile) {
-        const int y0 = t * c->tile_rows, rows = std::min(c->tile_rows, c->H - y0);
-        VR_CUDA(cudaMemcpyAsync(host_full_frame + (size_t)y0 * row_floats,
-                                c->d_frame + (size_t)local_tile * c->tile_rows * row_floats,
-                                (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    int rc;
+    if (banding_pays(c)) {
+        rc = render_banded(c, host_full_frame, stats);
+        if (rc != VR_OK) return rc;
+    } else {
+        rc = render_common(c, c->d_frame, /*compact=*/1, c->stream, stats);     // compact tiles fit in the frame buffer
+        if (rc != VR_OK) return rc;
+        const int tiles = (c->H + c->tile_rows - 1) / c->tile_rows;
+        const size_t row_floats = (size_t)c->W * 4;
+        int local_tile = 0;
+        for (int t = c->rank; t < tiles; t += c->world, ++local_tile) {
+            const int y0 = t * c->tile_rows, rows = std::min(c->tile_rows, c->H - y0);
+            VR_CUDA(cudaMemcpyAsync(host_full_frame + (size_t)y0 * row_floats,
+                                    c->d_frame + (size_t)local_tile * c->tile_rows * row_floats,
+                                    (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+        VR_CUDA(cudaStreamSynchronize(c->stream));
     }
-    VR_CUDA(cudaStreamSynchronize(c->stream));
     if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return VR_OK;
 }
@@ -1113,14 +1217,27 @@ static unsigned int* frame_sync_words(const vr_context* c, float* d_target_frame
     return reinterpret_cast<unsigned int*>(d_target_frame + (size_t)c->W * c->H * 4);
 }
 
+// a barrier wait of an earlier frame gave up: refuse to go on until the caller has looked (vr_peer_frame_reset)
+static int peer_error_check(const vr_context* c, const char* who)
+{
+    const unsigned int e = *(volatile unsigned int*)c->h_peer_error;
+    if (e == 0) return VR_OK;
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "%s: an earlier peer-frame wait (%s) timed out -- the frame may be torn; call vr_peer_frame_reset",
+                  who, e == 1 ? "arrivals" : "release");
+    return fail(VR_ERR_TIMEOUT, buf);
+}
+
 int vr_peer_frame_arrive(vr_context* c, float* d_target_frame, uint32_t frame_no, int world, int is_owner, void* cuda_stream)
 {
     if (!c || !d_target_frame || world < 1) return fail(VR_ERR_INVALID, "vr_peer_frame_arrive: bad argument");
+    int rc = peer_error_check(c, "vr_peer_frame_arrive");
+    if (rc != VR_OK) return rc;
     VR_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
     unsigned int* sync = frame_sync_words(c, d_target_frame);
     vr::peer_signal_kernel<<<1, 1, 0, s>>>(sync);
-    if (is_owner) vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, peer_timeout_ns());
+    if (is_owner) vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, peer_timeout_ns(), c->d_peer_error);
     VR_CUDA(cudaGetLastError());
     return VR_OK;
 }
@@ -1128,12 +1245,56 @@ int vr_peer_frame_arrive(vr_context* c, float* d_target_frame, uint32_t frame_no
 int vr_peer_frame_release(vr_context* c, float* d_target_frame, uint32_t frame_no, int is_owner, void* cuda_stream)
 {
     if (!c || !d_target_frame) return fail(VR_ERR_INVALID, "vr_peer_frame_release: bad argument");
+    int rc = peer_error_check(c, "vr_peer_frame_release");
+    if (rc != VR_OK) return rc;
     VR_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
     unsigned int* sync = frame_sync_words(c, d_target_frame);
     if (is_owner) vr::peer_release_kernel<<<1, 1, 0, s>>>(sync, frame_no);
-    else          vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 1, frame_no, peer_timeout_ns());
+    else          vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 1, frame_no, peer_timeout_ns(), c->d_peer_error);
     VR_CUDA(cudaGetLastError());
+    return VR_OK;
+}
+
+// render + arrive: the march kernel's last CTA publishes this rank's arrival (no signal kernel); kernels without
+// that epilogue (the generic loop) and ranks that own no row fall back to the one-thread signal kernel
+int vr_render_peer(vr_context* c, float* d_target_frame, uint32_t frame_no, int world, int is_owner, void* cuda_stream,
+                   vr_render_stats* stats)
+{
+    if (!c || !d_target_frame || world < 1) return fail(VR_ERR_INVALID, "vr_render_peer: bad argument");
+    int rc = peer_error_check(c, "vr_render_peer");
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    unsigned int* sync = frame_sync_words(c, d_target_frame);
+    LaunchPlan plan;
+    rc = make_plan(c, /*compact=*/0, &plan);
+    if (rc != VR_OK) return rc;
+    bool signalled = false;
+    VR_CUDA(cudaEventRecord(c->ev0, s));
+    rc = launch_march(c, plan, d_target_frame, 0, plan.local_rows, s, &sync[0], &signalled);
+    if (rc != VR_OK) return rc;
+    uint32_t launches = plan.local_rows > 0 ? 1u : 0u;
+    if (!signalled) { vr::peer_signal_kernel<<<1, 1, 0, s>>>(sync); ++launches; }
+    VR_CUDA(cudaEventRecord(c->ev1, s));
+    if (is_owner) { vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, peer_timeout_ns(), c->d_peer_error); ++launches; }
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    fill_stats(stats, ms, launches, plan);
+    if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
+int vr_peer_frame_reset(vr_context* c, float* d_target_frame)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_peer_frame_reset: null context");
+    VR_CUDA(cudaSetDevice(c->device));
+    VR_CUDA(cudaDeviceSynchronize());
+    *c->h_peer_error = 0;
+    if (d_target_frame) VR_CUDA(cudaMemset(frame_sync_words(c, d_target_frame) + 2, 0, sizeof(unsigned int)));
     return VR_OK;
 }
 
@@ -1183,8 +1344,11 @@ int vr_count_frame(vr_context* c, uint64_t* distinct_voxels, uint64_t* samples, 
     args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
     args.tf_lut = c->d_lut; args.out = c->d_frame; args.local_rows = plan.local_rows;
     args.touch_bits = d_bits; args.counters = d_cnt;
-    rc = c->bpv == 1 ? launch_direct_t<uint8_t, true>(c, plan, args, c->stream)
-                     : launch_direct_t<uint16_t, true>(c, plan, args, c->stream);
+    const dim3 grid((c->W + vr::DIRECT_BLOCK_W - 1) / vr::DIRECT_BLOCK_W, (plan.local_rows + vr::DIRECT_BLOCK_H - 1) / vr::DIRECT_BLOCK_H);
+    plan.fc.tc_div_mode = vr::DIV_IEEE;
+    rc = plan.local_rows == 0 ? VR_OK
+       : c->bpv == 1 ? launch_direct_t<uint8_t, true>(c, plan, args, grid, c->stream)
+                     : launch_direct_t<uint16_t, true>(c, plan, args, grid, c->stream);
     if (rc == VR_OK) {
         vr::popcount_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_bits, nwords, d_cnt + 2);
         unsigned long long h[3] = {0, 0, 0};

@@ -1,6 +1,8 @@
 // RendererCore.cpp -- see RendererCore.h.  Reference: src/RendererCore.cpp ("RC:n").
 #include "RendererCore.h"
 
+#include <exception>
+
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -170,8 +172,19 @@ bool RendererCore::saveImage(std::string fn, std::string ext)                   
 
 void RendererCore::readVolumeData(std::string fn)                                     // RC:242-447
 {
+    // nothing may escape into the GUI's frame loop: the reference reports through title/msg only (RC:264-301)
+    try {
+        readVolumeDataImpl(fn);
+    } catch (const std::exception& e) {
+        msg = std::string("Error reading volume: ") + e.what(); title = "Error!";
+    }
+}
+
+void RendererCore::readVolumeDataImpl(const std::string& fn)
+{
     const std::string ext = fn.length() >= 3 ? fn.substr(fn.length() - 3, 3) : std::string();
     std::vector<uint8_t> volume;
+    vr::MappedFile mapped;
     vr::PvmVolume pvm;
     const uint8_t* voxels = nullptr;
 
@@ -192,22 +205,36 @@ void RendererCore::readVolumeData(std::string fn)                               
             w.spacing[0] = voxel_size.x; w.spacing[1] = voxel_size.y; w.spacing[2] = voxel_size.z;
             vr::writeRawInf(fn, w);
         }
-        std::ifstream probe(fn, std::ios::binary);
-        if (!probe) { msg = "Failed to Open RAW file..."; title = "Error!"; return; }
-        const int64_t len = (int64_t)tex3D_dim.x * tex3D_dim.y * tex3D_dim.z;     // 64-bit (RC:327 overflows)
-        if (len <= 0) {
+        std::string merr;
+        if (!mapped.open(fn, merr)) { msg = "Failed to Open RAW file..."; title = "Error!"; return; }
+        if (tex3D_dim.x <= 0 || tex3D_dim.y <= 0 || tex3D_dim.z <= 0) {
             msg = "Texture Dimensions shouldn't contain any zeroes. Please provide a valid .raw.inf file.";
             title = "Invalid Data Size!";
             return;
         }
         if (datasize_bytes != 1 && datasize_bytes != 2) { msg = "Choose UINT8 or UINT16 first."; title = "Error!"; return; }
-        if (!vr::readRawPayload(fn, (uint64_t)len * (uint64_t)datasize_bytes, volume)) {
-            msg = "Failed to Open RAW file..."; title = "Error!"; return;
+        // 64-bit, range checked before anything is allocated (RC:327 multiplies into an `int`)
+        const uint64_t d64[3] = {(uint64_t)tex3D_dim.x, (uint64_t)tex3D_dim.y, (uint64_t)tex3D_dim.z};
+        uint64_t need = 0;
+        if (!vr::checkedVolumeBytes(d64, (uint64_t)datasize_bytes, need)) {
+            msg = "Texture Dimensions must be between 1 and 16384. Please provide a valid .raw.inf file.";
+            title = "Invalid Data Size!";
+            return;
         }
-        voxels = volume.data();
+        if (mapped.size() >= need) {
+            voxels = mapped.data();                     // zero-copy: the upload reads the mapped pages
+        } else {
+            // short file: the reference's value-initialised buffer leaves the tail at zero (RC:329-337)
+            volume.assign(need, 0);
+            if (mapped.size()) std::memcpy(volume.data(), mapped.data(), (size_t)mapped.size());
+            voxels = volume.data();
+        }
     } else {
         std::string err;
         if (!vr::pvmReadFile(fn, pvm, err)) { msg = "Error reading PVM file"; title = "Error!"; return; }
+        const uint64_t pd[3] = {pvm.width, pvm.height, pvm.depth};
+        uint64_t pbytes = 0;
+        if (!vr::checkedVolumeBytes(pd, 1, pbytes)) { msg = "Error reading PVM file"; title = "Error!"; return; }
         tex3D_dim = vr::ivec3{(int)pvm.width, (int)pvm.height, (int)pvm.depth};
         voxel_size = vr::vec3{pvm.scale[0], pvm.scale[1], pvm.scale[2]};
         if (datasize_bytes != 1 && datasize_bytes != 2) datasize_bytes = (int)pvm.components == 2 ? 2 : 1;

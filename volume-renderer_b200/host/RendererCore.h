@@ -71,6 +71,7 @@ public:
     vr_render_stats last_stats;
 
 private:
+    void readVolumeDataImpl(const std::string& fn);
     void pushParams();
     void reportAbiError(const char* title_text);
 };

@@ -8,6 +8,11 @@
 #include <fstream>
 #include <sstream>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace vr {
 
 // ------------------------------------------------------------------ .raw + .raw.inf
@@ -69,6 +74,40 @@ bool readRawPayload(const std::string& raw_fn, uint64_t n, std::vector<uint8_t>&
     if (!f) return false;
     out.assign(n, 0);
     f.read(reinterpret_cast<char*>(out.data()), (std::streamsize)n);
+    return true;
+}
+
+MappedFile::~MappedFile() { close(); }
+
+void MappedFile::close()
+{
+    if (data_ && size_) ::munmap(const_cast<uint8_t*>(data_), (size_t)size_);
+    data_ = nullptr; size_ = 0;
+}
+
+bool MappedFile::open(const std::string& fn, std::string& error)
+{
+    close();
+    const int fd = ::open(fn.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) { error = "cannot open " + fn + ": " + std::strerror(errno); return false; }
+    struct stat st;
+    if (::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); error = fn + " is not a regular file"; return false; }
+    if (st.st_size == 0) { ::close(fd); return true; }          // empty file: valid, nothing to map
+    void* p = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);                                                 // the mapping keeps the file alive
+    if (p == MAP_FAILED) { error = "mmap of " + fn + " failed: " + std::strerror(errno); return false; }
+    ::madvise(p, (size_t)st.st_size, MADV_SEQUENTIAL);
+    data_ = static_cast<const uint8_t*>(p); size_ = (uint64_t)st.st_size;
+    return true;
+}
+
+bool checkedVolumeBytes(const uint64_t dims[3], uint64_t bytes_per_voxel, uint64_t& bytes)
+{
+    bytes = 0;
+    if (bytes_per_voxel < 1 || bytes_per_voxel > 16) return false;
+    for (int i = 0; i < 3; ++i) if (dims[i] < 1 || dims[i] > kMaxVolumeDim) return false;
+    // 16384^3 * 16 = 2^46: cannot overflow once every factor is range checked
+    bytes = dims[0] * dims[1] * dims[2] * bytes_per_voxel;
     return true;
 }
 
@@ -293,13 +332,16 @@ bool pvmDecode(const uint8_t* file, uint64_t bytes, PvmVolume& out, std::string&
         return false;
     }
     if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) { error = "PVM: zero dimension"; return false; }
+    const uint64_t dims64[3] = {dims[0], dims[1], dims[2]};
     p = skipLine(p, end);
     uint32_t comps = 0;
     if (!p || !parseUInts(p, 1, &comps) || comps < 1) { error = "PVM: bad component count"; return false; }
     p = skipLine(p, end);
     if (!p) { error = "PVM: truncated header"; return false; }
 
-    const uint64_t vol = (uint64_t)dims[0] * dims[1] * dims[2] * comps;
+    // untrusted header: range-check every factor before multiplying (each can be up to 2^32 - 1)
+    uint64_t vol = 0;
+    if (!checkedVolumeBytes(dims64, comps, vol)) { error = "PVM: dimensions outside [1,16384] or more than 16 components"; return false; }
     if ((uint64_t)(end - p) < vol) { error = "PVM: payload shorter than width*height*depth*components"; return false; }
     const char* q = p + vol;
     std::string* strs[4] = {&out.description, &out.courtesy, &out.parameter, &out.comment};

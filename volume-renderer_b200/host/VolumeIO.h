@@ -25,6 +25,29 @@ bool writeRawInf(const std::string& raw_fn, const RawInf& inf);
 // Reads exactly n bytes (short files are zero filled like the reference's value-initialised buffer).
 bool readRawPayload(const std::string& raw_fn, uint64_t n, std::vector<uint8_t>& out);
 
+// Read-only memory map of a payload file (the `.raw` path of SURVEY.md 8f-3): no host copy of a multi-GiB
+// volume is made -- the pages stream from the page cache straight into the upload -- and every size is 64-bit
+// (the reference reads through `int len`, RendererCore.cpp:327, and fails above 2^31 voxels).
+class MappedFile {
+public:
+    MappedFile() = default;
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+    ~MappedFile();
+    bool open(const std::string& fn, std::string& error);
+    void close();
+    const uint8_t* data() const { return data_; }
+    uint64_t size() const { return size_; }
+private:
+    const uint8_t* data_ = nullptr;
+    uint64_t size_ = 0;
+};
+
+// per-dimension limit shared with the C-ABI upload (volren_b200.h: each dimension in [1,16384]) and an
+// overflow-checked byte count; false when a dimension is out of range or the product does not fit in 63 bits
+constexpr uint64_t kMaxVolumeDim = 16384;
+bool checkedVolumeBytes(const uint64_t dims[3], uint64_t bytes_per_voxel, uint64_t& bytes);
+
 struct PvmVolume {
     uint32_t width = 0, height = 0, depth = 0, components = 0;
     float scale[3] = {1.0f, 1.0f, 1.0f};

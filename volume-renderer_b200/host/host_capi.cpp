@@ -84,6 +84,22 @@ VRH_API const char* vrh_pvm_string(vrh_pvm* p, int which)
 VRH_API void vrh_pvm_free(vrh_pvm* p) { delete p; }
 VRH_API uint32_t vrh_dds_checksum(const uint8_t* data, uint64_t bytes) { return vr::ddsChecksum(data, bytes); }
 
+// read-only memory map of a payload file (the .raw path): size and single bytes at 64-bit offsets
+VRH_API vr::MappedFile* vrh_raw_map(const char* fn)
+{
+    vr::MappedFile* m = new vr::MappedFile();
+    std::string err;
+    if (!m->open(fn, err)) { delete m; return nullptr; }
+    return m;
+}
+VRH_API uint64_t vrh_raw_size(vr::MappedFile* m) { return m->size(); }
+VRH_API int vrh_raw_byte(vr::MappedFile* m, uint64_t offset) { return offset < m->size() ? (int)m->data()[offset] : -1; }
+VRH_API void vrh_raw_free(vr::MappedFile* m) { delete m; }
+VRH_API int vrh_checked_volume_bytes(const uint64_t dims[3], uint64_t bytes_per_voxel, uint64_t* bytes)
+{
+    return vr::checkedVolumeBytes(dims, bytes_per_voxel, *bytes) ? 1 : 0;
+}
+
 VRH_API int vrh_rawinf_write(const char* raw_fn, const int dims[3], const float spacing[3])
 {
     vr::RawInf inf;

@@ -19,8 +19,9 @@ LIB_PATH = os.environ.get("VOLREN_B200_LIB") or os.path.join(LIB_DIR, "libvolren
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libvolren_host.so")
 
 FILTER_NEAREST, FILTER_TRILINEAR = 0, 1
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOWED, KERNEL_FAST, KERNEL_TEXGATHER, KERNEL_TEXPAIR, KERNEL_TEXPAIR2, KERNEL_TEXPAIR_PIPE = 0, 1, 2, 3, 4, 5, 6, 7
-KERNEL_HYBRID, KERNEL_ZLSU, KERNEL_NEAREST_TEX = 8, 9, 10
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TEXPAIR_PIPE, KERNEL_NEAREST_TEX = 0, 1, 7, 10
+KERNEL_NAMES = {KERNEL_DIRECT: "march_direct_kernel", KERNEL_TEXPAIR_PIPE: "march_texpair_kernel", KERNEL_NEAREST_TEX: "march_nearest_kernel"}
+SKIP_AUTO, SKIP_ON, SKIP_OFF = 0, 1, 2
 
 VR_OK = 0
 
@@ -29,6 +30,7 @@ ABI_SYMBOLS = [
     "vr_version", "vr_last_error", "vr_params_default", "vr_device_count",
     "vr_create", "vr_destroy", "vr_resize", "vr_image_size",
     "vr_upload_volume", "vr_upload_volume_device", "vr_set_voxel_size", "vr_volume_stats_get",
+    "vr_cell_table_get", "vr_memory_info_get", "vr_render_peer", "vr_peer_frame_reset",
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
     "vr_render", "vr_read_frame", "vr_render_device", "vr_render_owned_to_host", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
     "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
@@ -54,12 +56,18 @@ class Params(C.Structure):
         ("use_tf", C.c_int32),
         ("tf_lut", C.c_float * 256),
         ("kernel", C.c_int32),
+        ("empty_skip", C.c_int32),
     ]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("kernel_used", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("kernel_used", C.c_uint32), ("skip_used", C.c_uint32)]
+
+
+class MemoryInfo(C.Structure):
+    _fields_ = [("linear_bytes", C.c_uint64), ("array_bytes", C.c_uint64), ("zpair_array_bytes", C.c_uint64),
+                ("cell_table_bytes", C.c_uint64), ("frame_bytes", C.c_uint64)]
 
 
 class VolumeStats(C.Structure):
@@ -118,6 +126,10 @@ def lib():
         L.vr_peer_frame_arrive.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p]
         L.vr_peer_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.vr_peer_frame_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.vr_render_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(RenderStats)]
+        L.vr_peer_frame_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.vr_cell_table_get.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int * 3), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.vr_memory_info_get.argtypes = [C.c_void_p, C.POINTER(MemoryInfo)]
         L.vr_count_frame.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.vr_upload_synthetic.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3), C.c_int, C.POINTER(C.c_float * 3),
                                           C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
@@ -304,6 +316,32 @@ class Context:
         a, r, t = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(lib().vr_peer_frame_status(self._h, C.c_void_p(target_ptr), C.byref(a), C.byref(r), C.byref(t)))
         return {"arrivals": a.value, "released": r.value, "timed_out": t.value}
+
+    def render_peer(self, target_ptr: int, frame_no: int, world: int, is_owner: bool, stream: int = 0):
+        """Render this rank's tiles into the (own or peer) frame; the kernel's last CTA signals the arrival."""
+        st = RenderStats()
+        _check(lib().vr_render_peer(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, world, 1 if is_owner else 0,
+                                    C.c_void_p(stream) if stream else None, C.byref(st)))
+        return st
+
+    def peer_frame_reset(self, target_ptr: int = 0):
+        _check(lib().vr_peer_frame_reset(self._h, C.c_void_p(target_ptr) if target_ptr else None))
+
+    def cell_table(self):
+        """-> dict(shift, cells (cx,cy,cz), mins[cz,cy,cx], maxs[cz,cy,cx], empty_cells under the current min_val)"""
+        sh, cells, ne = C.c_int(), (C.c_int * 3)(), C.c_uint64()
+        _check(lib().vr_cell_table_get(self._h, C.byref(sh), C.byref(cells), None, None, None))
+        n = cells[0] * cells[1] * cells[2]
+        mins, maxs = np.empty(n, np.uint16), np.empty(n, np.uint16)
+        _check(lib().vr_cell_table_get(self._h, C.byref(sh), C.byref(cells), mins.ctypes.data, maxs.ctypes.data, C.byref(ne)))
+        shape = (cells[2], cells[1], cells[0])
+        return {"shift": sh.value, "cells": tuple(cells[:]), "mins": mins.reshape(shape), "maxs": maxs.reshape(shape),
+                "empty_cells": ne.value}
+
+    def memory_info(self):
+        m = MemoryInfo()
+        _check(lib().vr_memory_info_get(self._h, C.byref(m)))
+        return {k: getattr(m, k) for k, _ in MemoryInfo._fields_}
 
     def read_rgb8(self, flip_vertical: bool = True) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), dtype=np.uint8)

@@ -41,6 +41,9 @@ def hlib():
             "vrh_pvm_error": ([vp], C.c_char_p), "vrh_pvm_header": ([vp, C.POINTER(C.c_uint32 * 5), C.POINTER(f * 3)], None),
             "vrh_pvm_payload_bytes": ([vp], C.c_uint64), "vrh_pvm_payload": ([vp], vp), "vrh_pvm_string": ([vp, i], C.c_char_p),
             "vrh_pvm_free": ([vp], None), "vrh_dds_checksum": ([vp, C.c_uint64], C.c_uint32),
+            "vrh_raw_map": ([C.c_char_p], vp), "vrh_raw_size": ([vp], C.c_uint64), "vrh_raw_byte": ([vp, C.c_uint64], i),
+            "vrh_raw_free": ([vp], None),
+            "vrh_checked_volume_bytes": ([C.POINTER(C.c_uint64 * 3), C.c_uint64, C.POINTER(C.c_uint64)], i),
             "vrh_rawinf_write": ([C.c_char_p, C.POINTER(C.c_int * 3), C.POINTER(f * 3)], i),
             "vrh_rawinf_read": ([C.c_char_p, C.POINTER(C.c_int * 3), C.POINTER(f * 3), C.c_char_p, C.c_char_p, i], i),
             "vrh_write_image": ([C.c_char_p, C.c_char_p, i, i, vp], i),
@@ -156,6 +159,34 @@ def pvm_decode(data: bytes = None, path: str = None):
 def dds_checksum(data: bytes) -> int:
     buf = np.frombuffer(data, dtype=np.uint8)
     return int(hlib().vrh_dds_checksum(buf.ctypes.data, buf.size))
+
+
+class MappedRaw:
+    """Read-only memory map of a .raw payload (host/VolumeIO.h MappedFile): 64-bit sizes, no host copy."""
+
+    def __init__(self, fn: str):
+        self._p = hlib().vrh_raw_map(fn.encode())
+        if not self._p:
+            raise OSError("cannot map " + fn)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            hlib().vrh_raw_free(self._p)
+            self._p = None
+
+    @property
+    def size(self) -> int:
+        return int(hlib().vrh_raw_size(self._p))
+
+    def byte(self, offset: int) -> int:
+        return int(hlib().vrh_raw_byte(self._p, int(offset)))
+
+
+def checked_volume_bytes(dims, bytes_per_voxel: int):
+    """-> byte count, or None when a dimension is outside [1,16384] (overflow-safe)."""
+    d = (C.c_uint64 * 3)(*[int(x) & 0xFFFFFFFFFFFFFFFF for x in dims])
+    out = C.c_uint64()
+    return int(out.value) if hlib().vrh_checked_volume_bytes(C.byref(d), int(bytes_per_voxel), C.byref(out)) else None
 
 
 def rawinf_write(raw_fn: str, dims, spacing) -> bool:
