@@ -15,12 +15,19 @@ e2e        same metric through the C-ABI render-to-host call: per frame the came
            block goes host->device and the finished RGBA32F frame comes back to pinned host
            memory inside the timed region.
 roofline   HBM bound: algorithmic bytes (2 B x distinct voxels referenced + 16 B x pixels)
-           / average march-kernel duration, against MEASURED_PEAKS.json's copy bandwidth.
-cpu_baseline  the CPU oracle (scalar port of the reference shader) on this box's host cores,
-           on a bounded sample of rows of the SAME frame; doubles as a full-size parity check.
+           / average march-kernel duration, against MEASURED_PEAKS.json's copy bandwidth;
+           `traffic` = DRAM bytes per launch from the ncu capture of THIS workload/kernel
+           (profiles/r02/traffic.json, written by tools/gpu/r2_profile.sh), else null.
+dense      the same frame with alpha so small that no ray reaches the 0.95 opacity threshold
+           (every ray marches through the whole box): the honest samples/s figure.
+cpu_baseline  the REFERENCE'S OWN SHADER compiled for the CPU (oracle/_ref/libshader_ref.so,
+           kind "reference"; the restated oracle, kind "port", when that is absent or the frame
+           uses an extension) on this box's host cores, on a bounded sample of rows of the SAME
+           frame; doubles as a full-size parity check.
 
---impl reference times the reference's own algorithm on the host cores (the reference's
-OpenGL path cannot run: no GL stack on this image) -- the oracle port, all host threads.
+--impl reference times the reference's own algorithm on the host cores (its OpenGL path cannot
+run: no GL stack on this image): VolumeRenderer.cs compiled for the CPU, all host threads.  That
+arm loads nothing but oracle/ libraries (input generated on the host).
 """
 from __future__ import annotations
 
@@ -39,7 +46,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mrays/sec at 1920x1080, 1024^3 uint16, 1024 steps"
 UNIT = "Mrays/s"
-TILE_ROWS = 16
+TILE_ROWS = 8            # = the CTA's 8 rows: 135 tiles over 8 ranks = 17 vs 16 (was 9 vs 8 with 16-row tiles)
+DENSE_ALPHA = 0.001      # 1 - (1 - 0.001)^1774 = 0.83 < 0.95: early-ray termination cannot fire
 
 
 def parse_args():
@@ -56,6 +64,9 @@ def parse_args():
     ap.add_argument("--cpu-row-stride", type=int, default=1, help="cpu_baseline renders every n-th row")
     ap.add_argument("--mip", action="store_true", help="maximum-intensity projection (the reference's use_mip toggle)")
     ap.add_argument("--tf", action="store_true", help="CubicSpline transfer function (default alpha knots of the reference's TF editor)")
+    ap.add_argument("--window", type=int, nargs=2, default=None, metavar=("MIN", "MAX"), help="window uniforms (default: the config's, SURVEY.md 8d)")
+    ap.add_argument("--skip", default="auto", choices=["auto", "on", "off"], help="result-identical empty-space skipping")
+    ap.add_argument("--no-dense", action="store_true", help="skip the extra dense (no early-ray-termination) measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-count", action="store_true", help="skip the distinct-voxel instrumentation pass")
     ap.add_argument("--handoff", default="peer", choices=["peer", "nccl"],
@@ -68,10 +79,12 @@ def workload(args):
     from volren_b200 import workloads
     cfg = dict(workloads.CONFIGS[args.config])
     cfg["seed"] = workloads.SEEDS[args.config]
-    cfg["window"] = (0, cfg["vmax"])
+    if args.window:
+        cfg["window"] = tuple(args.window)
     cfg["name"] = (f"{args.config}: {cfg['dims'][0]}x{cfg['dims'][1]}x{cfg['dims'][2]} uint{8 * cfg['bpv']} synthetic mix, "
-                   f"{cfg['image'][0]}x{cfg['image'][1]}, step_scale {cfg['step_scale']}, camera {args.camera}, "
+                   f"{cfg['image'][0]}x{cfg['image'][1]}, step_scale {cfg['step_scale']}, camera {args.camera}, window [{cfg['window'][0]},{cfg['window'][1]}], "
                    f"alpha {args.alpha}, {args.filter}" + (", CubicSpline TF" if args.tf else "") + (", MIP" if args.mip else ""))
+    cfg["key"] = f"{args.config}/{args.camera}/{args.filter}/{args.alpha}/{cfg['window'][0]}-{cfg['window'][1]}" + ("/tf" if args.tf else "") + ("/mip" if args.mip else "")
     return cfg
 
 
@@ -146,29 +159,49 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the march kernel from the committed ncu capture, if any."""
+def ncu_traffic(key, kernel):
+    """DRAM bytes per launch of the march kernel from the committed ncu capture of THIS workload (keyed by
+    config/camera/filter/alpha/window and kernel name), or None: never a number measured on another frame."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)
+        with open(os.path.join(ROOT, "profiles", "r02", "traffic.json")) as f:
+            ent = json.load(f).get(key)
+        if ent and ent.get("kernel") == kernel:
+            return ent.get("dram_bytes_per_launch")
     except Exception:
-        return None
+        pass
+    return None
 
 
-def cpu_march(cfg, args, host_vol, cam, row_stride, nthreads):
-    """The oracle on every row_stride-th row of the frame.  -> (Mrays/s, seconds, rows, image, counters)"""
+def tf_lut_cpu():
+    """The same LUT as default_tf_lut() from the oracle's spline (pinned to CubicSpline.cpp): no product library."""
+    from oracle import orc
+    return orc.OracleSpline([(0, 0.0), (141, 0.759), (149, 0.45), (255, 1.0)]).alpha_lut()
+
+
+def cpu_march(cfg, args, host_vol, cam, row_stride, nthreads, lut=None):
+    """The reference's own shader compiled for the CPU (or, for frames that use an extension, the restated oracle) on
+    every row_stride-th row of the frame.  -> (Mrays/s, seconds, rows, image, counters, kind)"""
     from oracle import orc
     W, H = cfg["image"]
     p = orc.make_params(W, H, cfg["dims"], cfg["bpv"], cam, alpha_scale=args.alpha,
                         min_val=cfg["window"][0], max_val=cfg["window"][1],
                         filter=1 if args.filter == "trilinear" else 0, step_scale=cfg["step_scale"],
-                        tf_lut=default_tf_lut() if args.tf else None, is_mip=1 if args.mip else 0,
+                        tf_lut=lut if args.tf else None, is_mip=1 if args.mip else 0,
                         row_begin=row_stride // 2, row_stride=row_stride)
+    use_ref = orc.ref_shader_lib() is not None and cfg["step_scale"] == 1.0 and not args.tf
     t0 = time.perf_counter()
-    img, cnt, _ = orc.render(p, host_vol, nthreads=nthreads)
+    if use_ref:
+        img, cnt = orc.ref_render(p, host_vol, nthreads=nthreads)
+    else:
+        img, cnt, _ = orc.render(p, host_vol, nthreads=nthreads)
     dt = time.perf_counter() - t0
     rows = np.arange(row_stride // 2, H, row_stride)
-    return rows.size * W / dt / 1e6, dt, rows, img, cnt
+    return rows.size * W / dt / 1e6, dt, rows, img, cnt, ("reference" if use_ref else "port")
+
+
+CPU_KIND_NOTE = {"reference": "the reference's own VolumeRenderer.cs compiled for the CPU (oracle/_ref/libshader_ref.so)",
+                 "port": "CPU restatement of VolumeRenderer.cs (oracle/march_oracle.c, pinned bit for bit to the reference shader); "
+                         "used because this frame needs an extension the shader lacks (step override / transfer function) or oracle/_ref is absent"}
 
 
 def run_reference(args):
@@ -176,23 +209,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = workload(args)
-    from volren_b200 import workloads
-    cam = workloads.camera_block(args.camera)
+    from oracle import orc
+    from volren_b200 import workloads          # pure numpy: loads no native library
+    cam = workloads.camera_block_const(args.camera)
     W, H = cfg["image"]
-    # input creation is not part of the timed path: use the GPU generator when there is one
-    host_vol = None
-    try:
-        import volren_b200 as vb
-        host_vol = vb.synthetic_to_host(cfg["dims"], cfg["bpv"], cfg["vmax"], cfg["seed"], True)
-    except Exception:
-        host_vol = workloads.mix_volume(cfg["dims"], cfg["vmax"], cfg["seed"], True)
     nthreads = os.cpu_count() or 1
+    # input creation is not part of the timed path; generated on the host cores so that this arm touches oracle/ only
+    host_vol = orc.synth_mix(cfg["dims"], cfg["bpv"], cfg["vmax"], cfg["seed"], True, nthreads)
+    lut = tf_lut_cpu() if args.tf else None
     stride = max(args.cpu_row_stride * 4, 1)
     for _ in range(args.warmup):
-        cpu_march(cfg, args, host_vol, cam, stride * 8, nthreads)        # short warm-up frames
-    times, rays = [], 0
+        cpu_march(cfg, args, host_vol, cam, stride * 8, nthreads, lut)        # short warm-up frames
+    times, rays, kind = [], 0, "port"
     for _ in range(args.steps):
-        v, dt, rows, _, _ = cpu_march(cfg, args, host_vol, cam, stride, nthreads)
+        v, dt, rows, _, _, kind = cpu_march(cfg, args, host_vol, cam, stride, nthreads, lut)
         times.append(dt); rays = rows.size * W
     total = float(sum(times))
     value = rays * args.steps / total / 1e6
@@ -201,9 +231,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "note": "reference OpenGL path not runnable (no GL stack); "
-                   "this is the CPU port of VolumeRenderer.cs (oracle/march_oracle.c)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "config": {"workload": cfg["name"], "note": "reference OpenGL path not runnable (no GL stack); this is " + CPU_KIND_NOTE[kind]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,7 +261,8 @@ def run_ours(args):
     params = vb.default_params(alpha_scale=args.alpha, min_val=cfg["window"][0], max_val=cfg["window"][1],
                                filter=vb.FILTER_TRILINEAR if args.filter == "trilinear" else vb.FILTER_NEAREST,
                                step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None,
-                               is_mip=1 if args.mip else 0)
+                               is_mip=1 if args.mip else 0,
+                               empty_skip={"auto": vb.SKIP_AUTO, "on": vb.SKIP_ON, "off": vb.SKIP_OFF}[args.skip])
 
     ctx = vb.Context(W, H, device=local_rank)
     want_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
@@ -258,7 +288,7 @@ def run_ours(args):
 
     kernel_ms = []
     launches = [0]
-    used = [0]
+    used = [0, 0]
 
     # fused hand-off: every rank maps rank 0's frame (NVLink peer memory) and renders into it
     peer_ptr = 0
@@ -283,15 +313,16 @@ def run_ours(args):
             st = ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
         elif handoff == "peer":
             # no collective call at all: completion and reuse of rank 0's frame are ordered by the
-            # barrier words behind its pixels (NVLink peer memory), two one-thread kernels per frame
+            # barrier words behind its pixels (NVLink peer memory); the arrival is published by the march kernel itself
             frame_no[0] += 1
             if rank != 0:
                 ctx.peer_frame_release(peer_ptr, frame_no[0] - 1, is_owner=False, stream=sptr)
-            st = ctx.render_device(peer_ptr, compact=False, stream=sptr)
-            ctx.peer_frame_arrive(peer_ptr, frame_no[0], world, is_owner=(rank == 0), stream=sptr)
+                launches[0] += 1
+            # the march kernel's last CTA publishes this rank's arrival (no signal kernel); rank 0 then waits for all
+            st = ctx.render_peer(peer_ptr, frame_no[0], world, is_owner=(rank == 0), stream=sptr)
             if rank == 0 and release:
                 ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)
-            launches[0] += 2
+                launches[0] += 1
         else:
             st = ctx.render_device(local.data_ptr(), compact=True, stream=sptr)
             vdist.gather_tiles(local, gathered, dst=0)
@@ -301,6 +332,7 @@ def run_ours(args):
         kernel_ms.append(st.kernel_ms)
         launches[0] += st.kernel_launches
         used[0] = st.kernel_used
+        used[1] = st.skip_used
 
     def barrier():
         if world > 1:
@@ -452,8 +484,7 @@ def run_ours(args):
     avg_kernel_ms = float(np.mean(timed_kernel_ms))
     peak, peak_src = measured_peak()
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "peak_source": peak_src, "kernel": {1: "march_direct_kernel", 2: "march_windowed_kernel", 3: "march_packed_kernel" if args.filter == "trilinear" else "march_fast_kernel", 4: "march_texgather_kernel",
-                                                    5: "march_texpair_kernel", 6: "march_texpair2_kernel", 7: "march_texpair_pipe_kernel", 8: "march_texpair_pipe_kernel", 9: "march_texpair_pipe_kernel", 10: "march_nearest_tex_kernel"}.get(used[0], "?"),
+            "peak_source": peak_src, "kernel": vb.KERNEL_NAMES.get(used[0], "?"), "empty_space_skipping": bool(used[1]),
             "kernel_ms_avg": avg_kernel_ms}
     if counted is not None:
         owned_px = sum(min(TILE_ROWS, H - t0_ * TILE_ROWS) for t0_ in range(rank, (H + TILE_ROWS - 1) // TILE_ROWS, world)) * W
@@ -465,19 +496,37 @@ def run_ours(args):
         roof["samples_per_launch"] = counted["samples"]
         roof["rays_hit"] = counted["rays_hit"]
         roof["gsamples_per_s"] = counted["samples"] / (avg_kernel_ms * 1e-3) / 1e9
-    tr = ncu_traffic()
-    if tr and tr.get("kernel") == roof["kernel"] and tr.get("workload_key") == f"{args.config}/{args.camera}/{args.filter}/{args.alpha}":
-        roof["traffic"] = tr.get("dram_bytes_per_launch")
+    roof["traffic"] = ncu_traffic(cfg["key"], roof["kernel"])
+    roof["workload_key"] = cfg["key"]
+
+    # the same frame without early-ray termination: every ray marches through the whole box
+    dense = None
+    if world == 1 and not args.no_dense and not args.mip:
+        dp = vb.default_params(alpha_scale=DENSE_ALPHA, min_val=cfg["window"][0], max_val=cfg["window"][1],
+                               filter=params.filter, step_scale=cfg["step_scale"], kernel=kernel, tf_lut=default_tf_lut() if args.tf else None,
+                               empty_skip=params.empty_skip)
+        ctx.set_params(dp)
+        dc = ctx.count_frame() if not args.no_count else None
+        for _ in range(3):
+            ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
+        dms = [ctx.render_device(frame.data_ptr(), compact=False, stream=sptr).kernel_ms for _ in range(10)]
+        dense = {"alpha": DENSE_ALPHA, "kernel_ms_avg": float(np.mean(dms)), "mrays_per_s": W * H / (float(np.mean(dms)) * 1e-3) / 1e6,
+                 "max_alpha_in_frame": float(frame[..., 3].max().item())}
+        if dc is not None:
+            dense["samples_per_launch"] = dc["samples"]
+            dense["gsamples_per_s"] = dc["samples"] / (dense["kernel_ms_avg"] * 1e-3) / 1e9
+            dense["roofline_frac"] = (bpv * dc["distinct_voxels"] + 16 * W * H) / (dense["kernel_ms_avg"] * 1e-3) / 1e9 / peak
+        ctx.set_params(params)
 
     cpu = None
     if want_cpu:
         nthreads = os.cpu_count() or 1
-        v, dt, rows_idx, img_cpu, cnt = cpu_march(cfg, args, host_vol, cam, args.cpu_row_stride, nthreads)
+        v, dt, rows_idx, img_cpu, cnt, kind = cpu_march(cfg, args, host_vol, cam, args.cpu_row_stride, nthreads, default_tf_lut() if args.tf else None)
         ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
         torch.cuda.synchronize()
         img_gpu = frame.cpu().numpy()
         err = float(np.abs(img_gpu[rows_idx].astype(np.float64) - img_cpu[rows_idx].astype(np.float64)).max())
-        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": kind, "what": CPU_KIND_NOTE[kind],
                "sample": f"every {args.cpu_row_stride}th row of the same {W}x{H} frame ({rows_idx.size * W} rays, "
                          f"{cnt['samples']} samples, {dt:.1f} s of CPU work on {nthreads} threads)",
                "parity_max_abs_err_on_sample": err,
@@ -490,13 +539,13 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, hand-off: "
-                                  + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory; frame barrier = flag words in the same peer memory (no collective call)", "nccl": "one NCCL gather + de-interleave"}[handoff],
+                                  + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory and their last CTA publishes the arrival in the frame barrier words of the same peer memory (no collective call, no signal kernel)", "nccl": "one NCCL gather + de-interleave"}[handoff],
                    "multi_gpu_frame_equals_single_gpu_frame": same_as_single,
                    "e2e_path": e2e_mode, "multi_gpu_host_frame_equals_single_gpu_frame": host_same,
                    "l2": f"inputs larger than L2 ({nvox * bpv / 2**30:.2f} GiB volume vs 126 MB L2); no flush needed" if nvox * bpv > 2**28
                          else "volume fits in L2 (correctness/plumbing config)",
                    "kernel": roof["kernel"]},
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "dense": dense, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": timed_launches, "clocks": clocks,

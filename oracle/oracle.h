@@ -79,6 +79,10 @@ void orc_frame_consts(const orc_params* p, float out[17]);
 /* Number of set bits in a touch bitmap of nvoxels bits. */
 uint64_t orc_popcount(const uint8_t* touch, uint64_t nvoxels);
 
+/* ---- synthetic volume `mix` on the host cores, x fastest; returns 0 or -1 ---- */
+int orc_synth_mix(void* out, const int32_t dims[3], int bytes_per_voxel, uint32_t vmax, uint32_t seed,
+                  int with_hash, int nthreads);
+
 /* ---- Camera (src/Camera.cpp) ---- */
 typedef struct orc_camera {
     float eye[4], side[4], up[4], look_at[4];

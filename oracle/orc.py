@@ -115,6 +115,8 @@ def lib():
         L.orc_checksum.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_checksum.restype = C.c_uint32
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_synth_mix.argtypes = [C.c_void_p, C.POINTER(C.c_int32 * 3), C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+        L.orc_synth_mix.restype = C.c_int
         _lib = L
     return _lib
 
@@ -246,6 +248,16 @@ def ref_render(p: Params, voxels: np.ndarray, *, nthreads: int = 1, out: np.ndar
     if rc != 0:
         raise ValueError("shader_ref_render: bad arguments")
     return out, {"rays": cnt.rays, "samples": cnt.samples}
+
+
+def synth_mix(dims, bytes_per_voxel: int, vmax: int, seed: int, with_hash: bool = True, nthreads: int = 0) -> np.ndarray:
+    """The `mix` volume of SURVEY.md 8(d) generated on the host cores (flat array, x fastest)."""
+    out = np.empty(int(dims[0]) * int(dims[1]) * int(dims[2]), dtype=np.uint8 if bytes_per_voxel == 1 else np.uint16)
+    d = (C.c_int32 * 3)(*[int(x) for x in dims])
+    if lib().orc_synth_mix(out.ctypes.data, C.byref(d), int(bytes_per_voxel), int(vmax), int(seed) & 0xFFFFFFFF,
+                           1 if with_hash else 0, int(nthreads) or (os.cpu_count() or 1)) != 0:
+        raise ValueError("orc_synth_mix: bad arguments")
+    return out
 
 
 def frame_consts(p: Params) -> np.ndarray:

@@ -17,6 +17,16 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    # the texture path: what the whole design argument rests on
+    "l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed", "l1tex__tex_writeback_active.sum",
+    "l1tex__data_pipe_tex_wavefronts.sum", "l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__texin_sm2tex_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_requests_pipe_tex.sum", "l1tex__t_sectors_pipe_tex.sum", "l1tex__t_sector_pipe_tex_hit_rate.pct",
+    "smsp__inst_executed_pipe_tex.sum", "smsp__thread_inst_executed.sum", "smsp__thread_inst_executed_pred_on.sum",
+    "smsp__warps_active.avg.per_cycle_active", "sm__inst_executed_pipe_fp32.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct",
+    "local_load_requests", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
 ]
 
 
@@ -45,6 +55,26 @@ def main():
     print(text)
     if len(sys.argv) > 2:
         open(sys.argv[2], "w").write(text + "\n")
+    # optional: record the DRAM traffic of the (last) kernel under a workload key for bench.py's roofline.traffic
+    if len(sys.argv) > 4:
+        import json
+        import os
+        tj, key = sys.argv[3], sys.argv[4]
+        d = dict(zip(hdr, rows[-1]))
+
+        def num(k):
+            try:
+                v = float(d[k].replace(",", ""))
+            except Exception:
+                return 0.0
+            u = units[hdr.index(k)].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        ent = {"kernel": d.get("Kernel Name", "?").split("(")[0].split("<")[0].replace("void vr::", "").strip(),
+               "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+               "source": os.path.basename(rep)}
+        allj = json.load(open(tj)) if os.path.exists(tj) else {}
+        allj[key] = ent
+        json.dump(allj, open(tj, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -67,7 +67,7 @@ def test_peer_stores_assemble_the_frame_in_rank0(tmp_path, world):
     assert np.load(out)[0] == 1
 
 
-def _worker_device_barrier(rank, world, port, out_path):
+def _worker_device_barrier(rank, world, port, out_path, fused=False):
     """Several frames back to back with NO host-side collective between them: completion and reuse of
     rank 0's frame are ordered only by the barrier words in peer memory (vr_peer_frame_arrive/release)."""
     sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
@@ -101,8 +101,15 @@ def _worker_device_barrier(rank, world, port, out_path):
             ctx.set_params(vb.default_params(alpha_scale=alphas[f - 1], min_val=0, max_val=255, filter=1))
             if rank != 0:
                 ctx.peer_frame_release(ptr, f - 1, is_owner=False)   # rank 0 is done with the previous frame
-            ctx.render_device(ptr, compact=False)
-            ctx.peer_frame_arrive(ptr, f, world, is_owner=(rank == 0))
+            if fused:
+                # vr_render_peer: the march kernel's last CTA publishes the arrival, no signal kernel
+                st = ctx.render_peer(ptr, f, world, is_owner=(rank == 0))
+                if st.kernel_launches != (2 if rank == 0 else 1):    # march (+ the owner's wait); never a signal kernel
+                    ok = 0
+                    print(f"rank {rank}: {st.kernel_launches} launches in the fused hand-off", flush=True)
+            else:
+                ctx.render_device(ptr, compact=False)
+                ctx.peer_frame_arrive(ptr, f, world, is_owner=(rank == 0))
             if rank == 0:
                 got = ctx.read_frame()                               # same stream: after the arrival wait
                 if not np.array_equal(got.view(np.uint32), refs[f - 1].view(np.uint32)):
@@ -123,7 +130,35 @@ def _worker_device_barrier(rank, world, port, out_path):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_peer_memory_frame_barrier(tmp_path, world):
+@pytest.mark.parametrize("fused", [False, True], ids=["signal_kernel", "fused_epilogue"])
+def test_peer_memory_frame_barrier(tmp_path, world, fused):
     out = str(tmp_path / "ok.npy")
-    mp.spawn(_worker_device_barrier, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker_device_barrier, args=(world, _free_port(), out, fused), nprocs=world, join=True)
     assert np.load(out)[0] == 1
+
+
+def test_a_barrier_timeout_is_reported_not_swallowed(monkeypatch):
+    """a wait that gives up must surface.  One process plays the owner of a 2-rank frame whose peer never
+    arrives: the bounded wait times out, the NEXT hand-off call fails with VR_ERR_TIMEOUT until the caller resets."""
+    sys.path[:0] = [os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    monkeypatch.setenv("VR_PEER_TIMEOUT_MS", "150")
+    import volren_b200 as vb
+    import scenarios
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    with vb.Context(96, 64) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(scenarios.camera("K0"))
+        ctx.set_params(vb.default_params(alpha_scale=0.1, min_val=0, max_val=255, filter=1))
+        ctx.set_partition(0, 2, 8)
+        ptr = ctx.frame_device_ptr()
+        ctx.render_peer(ptr, 1, 2, is_owner=True)            # arrivals stay at 1 of 2: the wait gives up after 150 ms
+        torch.cuda.synchronize()
+        assert ctx.peer_frame_status(ptr)["timed_out"] == 1
+        for call in (lambda: ctx.render_peer(ptr, 2, 2, is_owner=True), lambda: ctx.peer_frame_arrive(ptr, 2, 2, True),
+                     lambda: ctx.peer_frame_release(ptr, 1, True)):
+            with pytest.raises(vb.VolrenError) as e:
+                call()
+            assert e.value.code == -7 and "timed out" in str(e.value)
+        ctx.peer_frame_reset(ptr)
+        assert ctx.peer_frame_status(ptr)["timed_out"] == 0
+        ctx.peer_frame_release(ptr, 1, True)                 # works again

@@ -321,3 +321,10 @@ def test_read_volume_data_reports_bad_inf_dimensions_without_throwing(tmp_path):
     core.readVolumeData(fn)                  # no GPU needed: fails before any upload
     st = core.strings()
     assert st["title"] == "Invalid Data Size!" and "16384" in st["msg"]
+
+
+def test_stored_camera_blocks_equal_the_host_camera():
+    """workloads.camera_block_const (used by bench.py --impl reference, which must not load the product libraries)."""
+    from volren_b200 import workloads
+    for k in ("K0", "K1", "K2"):
+        assert np.array_equal(workloads.camera_block_const(k).view(np.uint32), workloads.camera_block(k).view(np.uint32))

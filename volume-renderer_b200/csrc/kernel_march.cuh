@@ -21,7 +21,8 @@
 // memory by every CTA) marks the cells (2^s voxels cubed, s chosen at upload) in which every voxel
 // a sample can touch is <= min_val; such a sample has v = 0 exactly (clamp, subtract min_val), adds
 // exactly 0 to both accumulators (alpha_scale >= 0, lut[0]*alpha == 0) and never wins a MIP
-// comparison, so neither its texels are fetched nor its arithmetic issued.  When the front of the
+// comparison, so neither its texels are fetched nor its arithmetic issued.  The map is consulted only
+// at checkpoints (every few samples, at a warp-uniform point of the loop), not per sample.  When the front of the
 // pipeline meets an empty cell it LEAPS: from the sample's exact index-space coordinate and the
 // ray's per-step increment it bounds (conservatively, 0.05 voxel inside the cell and the box) how
 // many further samples are certain to stay in that cell, then performs exactly that many position
@@ -278,11 +279,17 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, const M
     }
 }
 
-// The same march with empty-space skipping (see the file header).  `front` examines the sample at the front of
-// the pipeline: outside the box (or past the 10000-sample cap) -> the ray has no further sample; in an empty cell
-// -> leap (exact position updates only) and examine the landing sample; otherwise fetch it into a ring slot.
-// Skipped samples never enter the ring; they contribute exactly 0, so consuming the ring in order reproduces the
-// reference's accumulation sequence.
+// The same march with empty-space skipping (see the file header).  The pipelined loop is kept as it is; the cell
+// map is consulted only at CHECKPOINTS: the first sample and then every SKIP_CHECK_EVERY-th pass of the unrolled
+// loop -- a WARP-UNIFORM condition, so lanes never wait for each other's checkpoints.  At a checkpoint `examine`
+// looks at the front sample's cell.  Non-empty: carry on.  Empty: leap -- the number of further samples certain to
+// stay in the cell (a LOWER bound, 0.05 voxel inside the cell and the box) is skipped by performing exactly that
+// many position updates (:136), then the landing sample is examined in full (box test :118, cell test) and so on
+// until a non-empty cell or the end of the box.  Skipped samples never enter the ring; they contribute exactly 0,
+// so consuming the ring in order reproduces the reference's accumulation sequence.  (Samples of an empty cell
+// met between two checkpoints are simply processed: always exact, only slower.)
+constexpr int SKIP_CHECK_EVERY = 4;
+
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH>
 __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, const MarchArgs& args, const uint32_t* __restrict__ s_mask,
                                                        const float pos0[3], const float dstep[3], float& C, float& A)
@@ -296,55 +303,62 @@ __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, co
     const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
     const float nz = fc.dimf[2];
     const f2 mhalf = splat2(-0.5f);
-    float dux, duy, duz;
-    index_increments<FORM>(fc, dstep, dux, duy, duz);
-    int jf = 0;                                                          // index of the front sample (:115)
+    const unsigned last_layer = (unsigned)fc.dim[2];
+    int jf = 0;                                                          // index of the front sample (:115; only read when !NOCAP)
 
-    auto front = [&](FetchedPair& f) -> bool {
-        for (;;) {
-            f2 txy; float tz;
-            if (tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) > 0x3F800000u) return false;          // :118
-            if (!NOCAP && jf >= 10000) return false;                                                          // :115
+    // checkpoint: leap over the empty cells in front of the ray; on return (txy, tz, ok) describe the new front sample
+    auto examine = [&](f2& txy, float& tz, bool& ok) {
+        while (ok) {
             const f2 fxy = ffma(txy, nxy, mhalf);
             const float fz = __fmaf_rn(tz, nz, -0.5f);
             const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
-            if (!cell_is_empty(s_mask, args, (unsigned)(ix + 1), (unsigned)(iy + 1), (unsigned)(iz + 1))) {
-                const float flx = (float)ix, fly = (float)iy;
-                tld4_pair(tex, iz + 1, flx, fly, f.t01, f.t11, f.t10, f.t00);                                 // inside the box: layer in [0, Nz]
-                f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
-                return true;
-            }
+            if (!cell_is_empty(s_mask, args, (unsigned)(ix + 1), (unsigned)(iy + 1), (unsigned)(iz + 1))) return;
             // empty cell: this sample and the next k are certain to contribute nothing
+            float dux, duy, duz;
+            index_increments<FORM>(fc, dstep, dux, duy, duz);
             const float st = fminf(fminf(axis_steps(lo(fxy), (unsigned)(ix + 1), dux, args.cell_shift, -0.5f, fc.dimf[0] - 0.5f),
                                          axis_steps(hi(fxy), (unsigned)(iy + 1), duy, args.cell_shift, -0.5f, fc.dimf[1] - 0.5f)),
                                    axis_steps(fz, (unsigned)(iz + 1), duz, args.cell_shift, -0.5f, fc.dimf[2] - 0.5f));
             const int k = st > 0.0f ? (int)fminf(st, 65535.0f) : 0;
             for (int n = 0; n <= k; ++n) { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); }                    // :136, k+1 times
             if (!NOCAP) jf += k + 1;
+            ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                       // :118 of the landing sample
         }
     };
-    auto step = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };                    // :136
+    // the front stage: box test of the sample at `pos`, (checkpoint,) gather -- unconditional, like the plain loop
+    auto front = [&](FetchedPair& f, bool checkpoint) -> bool {
+        f2 txy; float tz;
+        bool ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                      // :118
+        if (checkpoint) examine(txy, tz, ok);
+        if (!NOCAP) ok = ok && jf < 10000;                                                                    // :115
+        const f2 fxy = ffma(txy, nxy, mhalf);
+        const float fz = __fmaf_rn(tz, nz, -0.5f);
+        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
+        const float flx = (float)ix, fly = (float)iy;
+        tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
+        f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
+        return ok;
+    };
+    auto advance = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };                // :136
 
     if (__float_as_uint(A) >= 0x3F733333u) return;
     FetchedPair F[DEPTH];
-    bool valid[DEPTH];
-    valid[0] = front(F[0]);
-    if (!valid[0]) return;
+    bool inside[DEPTH];
+    inside[0] = front(F[0], true);
+    if (!inside[0]) return;
 #pragma unroll
-    for (int k = 1; k < DEPTH - 1; ++k) {
-        valid[k] = valid[k - 1];
-        if (valid[k]) { step(); valid[k] = front(F[k]); }
-    }
-    bool go = true;
-    while (go) {
+    for (int k = 1; k < DEPTH - 1; ++k) { advance(); inside[k] = front(F[k], false); }
+    for (int it = 1;; ++it) {
+        bool go = true;
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
-            const int fill = (k + DEPTH - 1) % DEPTH, prev = (k + DEPTH - 2) % DEPTH, next = (k + 1) % DEPTH;
-            valid[fill] = DEPTH == 2 ? true : valid[prev];
-            if (valid[fill]) { step(); valid[fill] = front(F[fill]); }
+            const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
+            advance();
+            inside[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
             consume_pair<T, WIN, FORM>(fc, args, F[k], C, A);
-            if (!(valid[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
+            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
         }
+        if (!go) break;
     }
 }
 
@@ -448,7 +462,7 @@ __device__ __forceinline__ void march_ray_nearest(const FrameConsts& fc, const M
     }
 }
 
-// nearest filter with empty-space skipping: same front / leap logic as march_ray_texpair_skip; the index
+// nearest filter with empty-space skipping: same checkpoint / leap logic as march_ray_texpair_skip; the index
 // coordinate is u = t*N (the voxel is floor(u), clamped), the :118 range is u in [0, N]
 template <int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH>
 __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, const MarchArgs& args, const uint32_t* __restrict__ s_mask,
@@ -463,30 +477,41 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
     const f2 nxy = mk2(fc.dimf[0], fc.dimf[1]);
     const float nz = fc.dimf[2];
     const unsigned mx = (unsigned)fc.dim[0] - 1u, my = (unsigned)fc.dim[1] - 1u, mz = (unsigned)fc.dim[2] - 1u;
-    float dux, duy, duz;
-    index_increments<FORM>(fc, dstep, dux, duy, duz);
     int jf = 0;
 
-    auto front = [&](uint32_t& texel) -> bool {
-        for (;;) {
-            f2 txy; float tz;
-            if (tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) > 0x3F800000u) return false;          // :118
-            if (!NOCAP && jf >= 10000) return false;                                                          // :115
+    auto examine = [&](f2& txy, float& tz, bool& ok) {
+        while (ok) {
             const f2 uxy = fmul(txy, nxy);
             const float uz = __fmul_rn(tz, nz);
             const unsigned ix = min((unsigned)__float2int_rd(lo(uxy)), mx);
             const unsigned iy = min((unsigned)__float2int_rd(hi(uxy)), my);
             const unsigned iz = min((unsigned)__float2int_rd(uz), mz);
-            if (!cell_is_empty(s_mask, args, ix + 1u, iy + 1u, iz + 1u)) { texel = tld_layer(tex, iz, ix, iy); return true; }
+            if (!cell_is_empty(s_mask, args, ix + 1u, iy + 1u, iz + 1u)) return;
+            float dux, duy, duz;
+            index_increments<FORM>(fc, dstep, dux, duy, duz);
             const float st = fminf(fminf(axis_steps(lo(uxy), ix + 1u, dux, args.cell_shift, 0.0f, fc.dimf[0]),
                                          axis_steps(hi(uxy), iy + 1u, duy, args.cell_shift, 0.0f, fc.dimf[1])),
                                    axis_steps(uz, iz + 1u, duz, args.cell_shift, 0.0f, fc.dimf[2]));
             const int k = st > 0.0f ? (int)fminf(st, 65535.0f) : 0;
             for (int n = 0; n <= k; ++n) { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); }                    // :136, k+1 times
             if (!NOCAP) jf += k + 1;
+            ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
         }
     };
-    auto step = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };
+    auto front = [&](uint32_t& texel, bool checkpoint) -> bool {
+        f2 txy; float tz;
+        bool ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                      // :118
+        if (checkpoint) examine(txy, tz, ok);
+        if (!NOCAP) ok = ok && jf < 10000;                                                                    // :115
+        const f2 uxy = fmul(txy, nxy);
+        const float uz = __fmul_rn(tz, nz);
+        const unsigned ix = min((unsigned)__float2int_rd(lo(uxy)), mx);
+        const unsigned iy = min((unsigned)__float2int_rd(hi(uxy)), my);
+        const unsigned iz = min((unsigned)__float2int_rd(uz), mz);
+        texel = tld_layer(tex, iz, ix, iy);
+        return ok;
+    };
+    auto advance = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };
     auto consume = [&](uint32_t texel) {
         const float s = __fsub_rn(__uint_as_float(0x4B000000u | texel), 8388608.0f);
         shade_sample<WIN, FORM>(fc, args, s, C, A);
@@ -494,24 +519,22 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
 
     if (__float_as_uint(A) >= 0x3F733333u) return;
     uint32_t F[DEPTH];
-    bool valid[DEPTH];
-    valid[0] = front(F[0]);
-    if (!valid[0]) return;
+    bool inside[DEPTH];
+    inside[0] = front(F[0], true);
+    if (!inside[0]) return;
 #pragma unroll
-    for (int k = 1; k < DEPTH - 1; ++k) {
-        valid[k] = valid[k - 1];
-        if (valid[k]) { step(); valid[k] = front(F[k]); }
-    }
-    bool go = true;
-    while (go) {
+    for (int k = 1; k < DEPTH - 1; ++k) { advance(); inside[k] = front(F[k], false); }
+    for (int it = 1;; ++it) {
+        bool go = true;
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
-            const int fill = (k + DEPTH - 1) % DEPTH, prev = (k + DEPTH - 2) % DEPTH, next = (k + 1) % DEPTH;
-            valid[fill] = DEPTH == 2 ? true : valid[prev];
-            if (valid[fill]) { step(); valid[fill] = front(F[fill]); }
+            const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
+            advance();
+            inside[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
             consume(F[k]);
-            if (!(valid[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
+            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
         }
+        if (!go) break;
     }
 }
 

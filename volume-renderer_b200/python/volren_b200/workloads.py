@@ -41,6 +41,23 @@ def mix_volume(dims, vmax: int, seed: int, with_hash: bool = True, dtype=None) -
     return out.reshape(-1)
 
 
+# The three camera blocks as bit patterns (what camera_block() returns; tests/test_host.py keeps them in sync), so
+# that a CPU-only consumer -- bench.py --impl reference -- needs neither the host library nor the CUDA library.
+_CAMERA_BITS = {
+    "K0": [0x3f800000, 0x0, 0x0, 0x0, 0x0, 0x3f800000, 0x0, 0x0, 0x80000000, 0x80000000, 0x3f800000, 0x80000000,
+           0x0, 0x0, 0x40400000, 0x3f800000, 0x0, 0x0, 0x40400000, 0x3f800000, 0x406ed9ec],
+    "K1": [0x3f51b3f3, 0x0, 0xbf12d5e7, 0x0, 0xbe92d5e6, 0x3f5db3d7, 0xbed1b3f2, 0x0, 0x3efe53a0, 0x3efffffe, 0x3f359baa,
+           0x80000000, 0x3fbebeb9, 0x3fbfffff, 0x400834c0, 0x3f800000, 0x3fbebeb9, 0x3fbfffff, 0x400834c0, 0x3f800000, 0x406ed9ec],
+    "K2": [0xbf708fb3, 0x0, 0x3eaf1d44, 0x0, 0x3def920c, 0x3f708fb2, 0x3ea48dbb, 0x0, 0xbea48dba, 0x3eaf1d43, 0xbf620dbe,
+           0x80000000, 0xbf03a496, 0x3f0c176a, 0xbfb4d7cc, 0x3f800000, 0xbf03a496, 0x3f0c176a, 0xbfb4d7cc, 0x3f800000, 0x406ed9ec],
+}
+
+
+def camera_block_const(kind: str) -> np.ndarray:
+    """camera_block(kind) from the stored bit patterns: no native library involved."""
+    return np.array(_CAMERA_BITS[kind], dtype=np.uint32).view(np.float32).copy()
+
+
 def camera_block(kind: str) -> np.ndarray:
     """The 21-float camera block for K0 (reset), K1 (zenith 60, azimuth 35, r 3), K2 (zenith 70,
     azimuth 200, r 1.6), built by the product's host Camera."""
@@ -59,9 +76,10 @@ def camera_block(kind: str) -> np.ndarray:
 
 CONFIGS = {
     # name: dims, bytes/voxel, vmax, image, step_scale (reference step * scale), notes
-    "C1": dict(dims=(64, 64, 64), bpv=1, vmax=255, image=(256, 256), step_scale=0.5),
-    "C2": dict(dims=(256, 256, 256), bpv=1, vmax=255, image=(1024, 1024), step_scale=0.5),
-    "C3": dict(dims=(512, 512, 512), bpv=2, vmax=4095, image=(1920, 1080), step_scale=0.5),
-    "C4": dict(dims=(1024, 1024, 1024), bpv=2, vmax=4095, image=(1920, 1080), step_scale=1.0),
-    "C5": dict(dims=(2048, 2048, 1024), bpv=2, vmax=4095, image=(3840, 2160), step_scale=1.0),
+    # `window` = the uniform values of SURVEY.md 8(d)'s table (C3: GUI 0..2000 + the reference's +1000 rule)
+    "C1": dict(dims=(64, 64, 64), bpv=1, vmax=255, image=(256, 256), step_scale=0.5, window=(0, 255)),
+    "C2": dict(dims=(256, 256, 256), bpv=1, vmax=255, image=(1024, 1024), step_scale=0.5, window=(0, 255)),
+    "C3": dict(dims=(512, 512, 512), bpv=2, vmax=4095, image=(1920, 1080), step_scale=0.5, window=(1000, 3000)),
+    "C4": dict(dims=(1024, 1024, 1024), bpv=2, vmax=4095, image=(1920, 1080), step_scale=1.0, window=(0, 4095)),
+    "C5": dict(dims=(2048, 2048, 1024), bpv=2, vmax=4095, image=(3840, 2160), step_scale=1.0, window=(0, 4095)),
 }
