@@ -30,4 +30,4 @@ cap texpair_C3_skip    march_texpair_kernel "C3/K2/trilinear/0.05/1000-3000" --c
 cap texpair_C2         march_texpair_kernel "C2/K2/trilinear/0.02/0-255" --config C2
 cap texpair_C5         march_texpair_kernel "C5/K2/trilinear/0.02/0-4095" --config C5
 ls -la $O | head -40
-cuobjdump -sass -fun $(cuobjdump -elf volume-renderer_b200/lib/libvolren_b200.so | grep -o "_ZN2vr20march_texpair_kernelItLi0ELi1ELb1ELb1ELi0ELi3ELb0ELi4EEEvNS_11FrameConstsENS_9MarchArgsE" | head -1) volume-renderer_b200/lib/libvolren_b200.so > $O/sass_texpair_headline.txt 2>&1
+cuobjdump -sass -fun $(cuobjdump -elf volume-renderer_b200/lib/libvolren_b200.so | grep -o "_ZN2vr20march_texpair_kernelItLi0ELi1ELb1ELb1ELi0ELi4ELb0ELi4EEEvNS_11FrameConstsENS_9MarchArgsE" | head -1) volume-renderer_b200/lib/libvolren_b200.so > $O/sass_texpair_headline.txt 2>&1

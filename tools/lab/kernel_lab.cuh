@@ -1,4 +1,5 @@
-// kernel_fast.cuh -- issue-slot-optimised form of the reference march for the common case
+// kernel_lab.cuh (round 1: csrc/kernel_fast.cuh) -- DEVELOPMENT KERNELS, not part of the product library.
+// issue-slot-optimised form of the reference march for the common case
 // (DVR, default view, no transfer function, ordered window, alpha_scale >= 0).
 //
 // Same correctly-rounded operation sequence as march_device.cuh / the oracle -- results are
@@ -11,22 +12,11 @@
 // through the device-verified Markstein sequence.
 #pragma once
 
+#include "f32x2.cuh"
 #include "march_device.cuh"
 
 namespace vr {
 
-typedef unsigned long long u64;
-
-// ---- packed pair of floats: lane .x = ray 0 (even pixel), lane .y = ray 1 (odd pixel) -------
-struct f2 { u64 v; };
-__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ f2 splat2(float a) { return mk2(a, a); }
-__device__ __forceinline__ float lo(f2 p) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return a; }
-__device__ __forceinline__ float hi(f2 p) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); return b; }
-__device__ __forceinline__ f2 fadd(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 fsub(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 fmul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 ffma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
 // ptxas (12.9) contracts mul.rn.f32x2 -> add/sub.rn.f32x2 into FFMA2 even under -fmad=false
 // (it honours the explicit .rn only on scalar ops).  Wherever the shader has an UNFUSED
 // product feeding a sum, the sum is therefore issued as two scalar add.rn.f32.

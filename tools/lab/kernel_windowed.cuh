@@ -21,7 +21,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
-#include "kernel_fast.cuh"
+#include "kernel_lab.cuh"
 
 namespace vr {
 

@@ -2,7 +2,9 @@
 // (1024^3 uint16 synthetic mix, 1920x1080, camera K2, alpha 0.02, trilinear) on one GPU, checks
 // each variant bit-for-bit against the baseline direct kernel (which the pytest suite checks
 // against the CPU oracle) and prints CUDA-event timings.  Development tool, not product.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -lineinfo -I../include -I../volume-renderer_b200/csrc marchlab.cu -o marchlab
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 --fmad=false -lineinfo -I../../include -I../../volume-renderer_b200/csrc -I. marchlab.cu -o marchlab
+// Holds the round-1 development kernels that were measured slower than the product's two (kernel_lab.cuh: LSU "fast" /
+// "packed", two-gather, non-pipelined and two-ray z-pair, hybrid TEX+LSU; kernel_windowed.cuh: TMA-staged windows).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,8 +16,9 @@
 #include "frame.h"
 #include "march_device.cuh"
 #include "kernel_direct.cuh"
-#include "kernel_fast.cuh"
+#include "kernel_lab.cuh"
 #include "kernels_aux.cuh"
+#include "lab_aux.cuh"
 #include "kernel_windowed.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
@@ -164,7 +167,7 @@ int main(int argc, char** argv)
     L.pitch = (uint32_t)(((uint64_t)(N + 2) * 2 + 15) / 16 * 16 / 2);
     L.slice = (uint64_t)L.pitch * (N + 2);
     CK(cudaMalloc(&L.d_pad, L.slice * (N + 2) * 2 + 256));
-    pad_volume_kernel<uint16_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pad, N, N, N, L.pitch);
+    lab::pad_volume_kernel<uint16_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pad, N, N, N, L.pitch);
     {   // layered 2-D array + point-sampling texture object for the gather variant
         cudaChannelFormatDesc cd = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
         CK(cudaMalloc3DArray(&L.arr, &cd, make_cudaExtent(N, N, N), cudaArrayLayered));
@@ -195,7 +198,7 @@ int main(int argc, char** argv)
         CK(cudaCreateTextureObject(&L.texf, &rd, &td, nullptr));
     }
     CK(cudaMalloc(&L.d_pairs, L.slice * (N + 2) * 4 + 256));
-    pad_pairs_kernel<uint16_t, uint32_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pairs, N, N, N, L.pitch);
+    lab::pad_pairs_kernel<uint16_t, uint32_t><<<prop.multiProcessorCount * 16, 256>>>(d_src, L.d_pairs, N, N, N, L.pitch);
     CK(cudaDeviceSynchronize());
     CK(cudaFree(d_src));
     CK(cudaMalloc(&L.d_ref, (size_t)L.W * L.H * 16)); CK(cudaMalloc(&L.d_out, (size_t)L.W * L.H * 16));

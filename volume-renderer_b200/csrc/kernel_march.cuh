@@ -83,7 +83,9 @@ __device__ __forceinline__ uint32_t tld_layer(cudaTextureObject_t tex, unsigned 
 }
 
 // biased floats 2^23 + v of the two halves of a z-pair texel: one PRMT each (differences of biased
-// values are exact, so only the x-low corners are un-biased, inside the lerp's addend)
+// values are exact, so only the x-low corners are un-biased, inside the lerp's addend).  (A sub-word
+// integer->float conversion, I2F.U16 Rx.H0/.H1, would save the un-biasing but runs on the 1/8-rate conversion
+// pipe: 8 per sample would make that pipe the bound.)
 template <typename T> __device__ __forceinline__ f2 unpack_zpair(uint32_t w);
 template <> __device__ __forceinline__ f2 unpack_zpair<uint16_t>(uint32_t w)
 {
@@ -239,12 +241,14 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, const M
     const f2 mhalf = splat2(-0.5f);
     const unsigned last_layer = (unsigned)fc.dim[2];
 
-    // texel coordinates, weights, gather
+    // texel coordinates, weights, gather.  x / y are only needed as floats (gather coordinate + weight): one
+    // FRND.FLOOR each; z is needed as the layer index: F2I.FLOOR + I2FP.  (floorf is exact, so the weights are the
+    // same single-rounded differences f - floor(f) as in the oracle.)
     auto fetch = [&](f2 txy, float tz, FetchedPair& f) {
         const f2 fxy = ffma(txy, nxy, mhalf);
         const float fz = __fmaf_rn(tz, nz, -0.5f);
-        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
-        const float flx = (float)ix, fly = (float)iy;
+        const float flx = floorf(lo(fxy)), fly = floorf(hi(fxy));
+        const int iz = __float2int_rd(fz);
         tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
         f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
     };
@@ -252,31 +256,35 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, const M
     f2 txy; float tz;
     if (tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return;   // :118, first sample
     FetchedPair F[DEPTH];
-    bool inside[DEPTH];
+    unsigned key[DEPTH];                                                 // :118 range key of the sample in each slot
     fetch(txy, tz, F[0]);
-    inside[0] = true;
+    key[0] = 0u;
 #pragma unroll
     for (int k = 1; k < DEPTH - 1; ++k) {                               // prologue: samples 1 .. DEPTH-2
         pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz);                    // :136
-        inside[k] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
+        key[k] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);
         fetch(txy, tz, F[k]);
     }
-    bool go = true;
-    for (int iter = 0; go && (NOCAP || iter < 10000); iter += DEPTH) {
+    int iter = 0;
+    // one pass of the unrolled ring; false = the ray is finished
+    auto pass = [&]() -> bool {
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             // look ahead: sample (iter + k) + DEPTH-1
             pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz);                // :136
-            inside[fill] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
+            key[fill] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);
             fetch(txy, tz, F[fill]);
             // finish sample iter + k
             consume_pair<T, WIN, FORM>(fc, args, F[k], C, A);
             // :118 of sample iter + k + 1 (the `dest.a > 0.99` break of :134 is subsumed by it: only `pos` changes in between)
-            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
-            if (!NOCAP && iter + k + 1 >= 10000) { go = false; break; } // :115
+            if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
+            if (!NOCAP && iter + k + 1 >= 10000) return false;           // :115
         }
-    }
+        iter += DEPTH;
+        return true;
+    };
+    while (pass()) {}
 }
 
 // The same march with empty-space skipping (see the file header).  The pipelined loop is kept as it is; the cell
@@ -306,9 +314,9 @@ __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, co
     const unsigned last_layer = (unsigned)fc.dim[2];
     int jf = 0;                                                          // index of the front sample (:115; only read when !NOCAP)
 
-    // checkpoint: leap over the empty cells in front of the ray; on return (txy, tz, ok) describe the new front sample
-    auto examine = [&](f2& txy, float& tz, bool& ok) {
-        while (ok) {
+    // checkpoint: leap over the empty cells in front of the ray; on return (txy, tz, key) describe the new front sample
+    auto examine = [&](f2& txy, float& tz, unsigned& key) {
+        while (key <= 0x3F800000u) {
             const f2 fxy = ffma(txy, nxy, mhalf);
             const float fz = __fmaf_rn(tz, nz, -0.5f);
             const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
@@ -322,44 +330,47 @@ __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, co
             const int k = st > 0.0f ? (int)fminf(st, 65535.0f) : 0;
             for (int n = 0; n <= k; ++n) { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); }                    // :136, k+1 times
             if (!NOCAP) jf += k + 1;
-            ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                       // :118 of the landing sample
+            key = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);                                     // :118 of the landing sample
         }
     };
-    // the front stage: box test of the sample at `pos`, (checkpoint,) gather -- unconditional, like the plain loop
-    auto front = [&](FetchedPair& f, bool checkpoint) -> bool {
+    // the front stage: box test of the sample at `pos`, (checkpoint,) gather -- unconditional, like the plain loop;
+    // returns the :118 range key of the sample now in the slot (> 1.0f's bit pattern: no such sample)
+    auto front = [&](FetchedPair& f, bool checkpoint) -> unsigned {
         f2 txy; float tz;
-        bool ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                      // :118
-        if (checkpoint) examine(txy, tz, ok);
-        if (!NOCAP) ok = ok && jf < 10000;                                                                    // :115
+        unsigned key = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);                                // :118
+        if (checkpoint) examine(txy, tz, key);
+        if (!NOCAP && jf >= 10000) key = 0xFFFFFFFFu;                                                         // :115
         const f2 fxy = ffma(txy, nxy, mhalf);
         const float fz = __fmaf_rn(tz, nz, -0.5f);
-        const int ix = __float2int_rd(lo(fxy)), iy = __float2int_rd(hi(fxy)), iz = __float2int_rd(fz);
-        const float flx = (float)ix, fly = (float)iy;
+        const float flx = floorf(lo(fxy)), fly = floorf(hi(fxy));
+        const int iz = __float2int_rd(fz);
         tld4_pair(tex, (int)min((unsigned)(iz + 1), last_layer), flx, fly, f.t01, f.t11, f.t10, f.t00);
         f.wx = __fsub_rn(lo(fxy), flx); f.wy = __fsub_rn(hi(fxy), fly); f.wz = __fsub_rn(fz, (float)iz);
-        return ok;
+        return key;
     };
     auto advance = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };                // :136
 
     if (__float_as_uint(A) >= 0x3F733333u) return;
     FetchedPair F[DEPTH];
-    bool inside[DEPTH];
-    inside[0] = front(F[0], true);
-    if (!inside[0]) return;
+    unsigned key[DEPTH];
+    key[0] = front(F[0], true);
+    if (key[0] > 0x3F800000u) return;
 #pragma unroll
-    for (int k = 1; k < DEPTH - 1; ++k) { advance(); inside[k] = front(F[k], false); }
-    for (int it = 1;; ++it) {
-        bool go = true;
+    for (int k = 1; k < DEPTH - 1; ++k) { advance(); key[k] = front(F[k], false); }
+    int it = 1;
+    auto pass = [&]() -> bool {
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             advance();
-            inside[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
+            key[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
             consume_pair<T, WIN, FORM>(fc, args, F[k], C, A);
-            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
+            if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
         }
-        if (!go) break;
-    }
+        ++it;
+        return true;
+    };
+    while (pass()) {}
 }
 
 // CTA = 256 threads = 32 x 8 pixels; a warp covers an 8 x 4 pixel patch.
@@ -438,28 +449,31 @@ __device__ __forceinline__ void march_ray_nearest(const FrameConsts& fc, const M
     f2 txy; float tz;
     if (tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return;
     uint32_t F[DEPTH];
-    bool inside[DEPTH];
+    unsigned key[DEPTH];
     F[0] = fetch(txy, tz);
-    inside[0] = true;
+    key[0] = 0u;
 #pragma unroll
     for (int k = 1; k < DEPTH - 1; ++k) {
         pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz);
-        inside[k] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
+        key[k] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);
         F[k] = fetch(txy, tz);
     }
-    bool go = true;
-    for (int iter = 0; go && (NOCAP || iter < 10000); iter += DEPTH) {
+    int iter = 0;
+    auto pass = [&]() -> bool {
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz);                // :136
-            inside[fill] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
+            key[fill] = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);
             F[fill] = fetch(txy, tz);
             consume(F[k]);
-            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
-            if (!NOCAP && iter + k + 1 >= 10000) { go = false; break; }
+            if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
+            if (!NOCAP && iter + k + 1 >= 10000) return false;
         }
-    }
+        iter += DEPTH;
+        return true;
+    };
+    while (pass()) {}
 }
 
 // nearest filter with empty-space skipping: same checkpoint / leap logic as march_ray_texpair_skip; the index
@@ -479,8 +493,8 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
     const unsigned mx = (unsigned)fc.dim[0] - 1u, my = (unsigned)fc.dim[1] - 1u, mz = (unsigned)fc.dim[2] - 1u;
     int jf = 0;
 
-    auto examine = [&](f2& txy, float& tz, bool& ok) {
-        while (ok) {
+    auto examine = [&](f2& txy, float& tz, unsigned& key) {
+        while (key <= 0x3F800000u) {
             const f2 uxy = fmul(txy, nxy);
             const float uz = __fmul_rn(tz, nz);
             const unsigned ix = min((unsigned)__float2int_rd(lo(uxy)), mx);
@@ -495,21 +509,21 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
             const int k = st > 0.0f ? (int)fminf(st, 65535.0f) : 0;
             for (int n = 0; n <= k; ++n) { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); }                    // :136, k+1 times
             if (!NOCAP) jf += k + 1;
-            ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;
+            key = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);
         }
     };
-    auto front = [&](uint32_t& texel, bool checkpoint) -> bool {
+    auto front = [&](uint32_t& texel, bool checkpoint) -> unsigned {
         f2 txy; float tz;
-        bool ok = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz) <= 0x3F800000u;                      // :118
-        if (checkpoint) examine(txy, tz, ok);
-        if (!NOCAP) ok = ok && jf < 10000;                                                                    // :115
+        unsigned key = tex_coord_key<TCDIV, UNIT, FORM>(fc, pxy, pz, txy, tz);                                // :118
+        if (checkpoint) examine(txy, tz, key);
+        if (!NOCAP && jf >= 10000) key = 0xFFFFFFFFu;                                                         // :115
         const f2 uxy = fmul(txy, nxy);
         const float uz = __fmul_rn(tz, nz);
         const unsigned ix = min((unsigned)__float2int_rd(lo(uxy)), mx);
         const unsigned iy = min((unsigned)__float2int_rd(hi(uxy)), my);
         const unsigned iz = min((unsigned)__float2int_rd(uz), mz);
         texel = tld_layer(tex, iz, ix, iy);
-        return ok;
+        return key;
     };
     auto advance = [&]() { pxy = fadd(pxy, dxy); pz = __fadd_rn(pz, dz); if (!NOCAP) ++jf; };
     auto consume = [&](uint32_t texel) {
@@ -519,23 +533,25 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
 
     if (__float_as_uint(A) >= 0x3F733333u) return;
     uint32_t F[DEPTH];
-    bool inside[DEPTH];
-    inside[0] = front(F[0], true);
-    if (!inside[0]) return;
+    unsigned key[DEPTH];
+    key[0] = front(F[0], true);
+    if (key[0] > 0x3F800000u) return;
 #pragma unroll
-    for (int k = 1; k < DEPTH - 1; ++k) { advance(); inside[k] = front(F[k], false); }
-    for (int it = 1;; ++it) {
-        bool go = true;
+    for (int k = 1; k < DEPTH - 1; ++k) { advance(); key[k] = front(F[k], false); }
+    int it = 1;
+    auto pass = [&]() -> bool {
 #pragma unroll
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             advance();
-            inside[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
+            key[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
             consume(F[k]);
-            if (!(inside[next] && __float_as_uint(A) < 0x3F733333u)) { go = false; break; }
+            if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
         }
-        if (!go) break;
-    }
+        ++it;
+        return true;
+    };
+    while (pass()) {}
 }
 
 template <int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH, bool SKIP, int MINB>

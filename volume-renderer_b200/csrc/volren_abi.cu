@@ -65,10 +65,10 @@ struct DevBuf {
 };
 
 // pipeline depth / resident CTAs per SM of the optimised kernels, measured on the headline frame
-// (lab r2: depth 3 at 64 registers / 4 CTAs per SM is the most robust choice across cameras, partitions, volume
+// (lab r2: depth 4 at 64 registers / 4 CTAs per SM is the best choice across cameras, partitions, volume
 // shapes; the skipping forms carry the leap state and want the same register budget)
 #ifndef VR_TP_DEPTH
-#define VR_TP_DEPTH 3
+#define VR_TP_DEPTH 4
 #endif
 #ifndef VR_TP_MINB
 #define VR_TP_MINB 4
