@@ -69,7 +69,7 @@ def main():
                 return 0.0
             u = units[hdr.index(k)].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-        ent = {"kernel": d.get("Kernel Name", "?").split("(")[0].split("<")[0].replace("void vr::", "").strip(),
+        ent = {"kernel": d.get("Kernel Name", "?").split("(")[0].split("<")[0].replace("void vr::", "").replace("void ", "").replace("vr::", "").strip(),
                "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                "source": os.path.basename(rep)}
         allj = json.load(open(tj)) if os.path.exists(tj) else {}

@@ -20,6 +20,8 @@ cap() {  # name kernel-regex workload-key bench-args...
   echo "ncu $name rc=$?"
   python profiles/summarize_ncu.py $O/ncu_$name.ncu-rep $O/ncu_${name}_summary.txt $O/traffic.json "$key" > /dev/null 2>&1
   head -n 3 $O/ncu_${name}_summary.txt
+  # gpurun_out/ is limited to 64 MiB: keep only the headline capture (source page), drop the other reports
+  if [ "$name" != "texpair_C4_K2" ]; then rm -f $O/ncu_$name.ncu-rep; else ncu -i $O/ncu_$name.ncu-rep --page source --csv > $O/ncu_${name}_source.csv 2>/dev/null; fi
 }
 cap texpair_C4_K2      march_texpair_kernel "C4/K2/trilinear/0.02/0-4095"
 cap texpair_C4_K0      march_texpair_kernel "C4/K0/trilinear/0.02/0-4095" --camera K0

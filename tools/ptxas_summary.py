@@ -6,6 +6,8 @@ import sys
 
 log = open(sys.argv[1] if len(sys.argv) > 1 else "volume-renderer_b200/lib/ptxas.log").read()
 ents = re.findall(r"Compiling entry function '([^']+)' for 'sm_100a'\n.*?\n.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log)
+if not ents:
+    print("no kernels found in the log (build error?)"); sys.exit(1)
 dem = subprocess.run(["cu++filt"] + [e[0] for e in ents], capture_output=True, text=True).stdout.splitlines()
 rows = []
 for (n, st, ss, sl, regs), d in zip(ents, dem):

@@ -373,19 +373,26 @@ __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, co
     while (pass()) {}
 }
 
-// CTA = 256 threads = 32 x 8 pixels; a warp covers an 8 x 4 pixel patch.
-template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH, bool SKIP, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+// A warp covers an 8 x 4 pixel patch; a CTA of CTAW warps covers (8 * min(CTAW,4)) x (4 * CTAW / min(CTAW,4)) pixels:
+// 8 warps = 32 x 8, 4 warps = 32 x 4, 2 warps = 16 x 4.  MINW = resident WARPS per SM the register budget is sized for.  Smaller CTAs return their registers sooner (a CTA lives as long as its slowest
+// warp) and balance the tail of small grids (multi-GPU partitions) at a finer grain.
+template <int CTAW, int WX_ = (CTAW < 4 ? CTAW : 4)> struct CtaShape {
+    static constexpr int WX = WX_, WY = CTAW / WX, PX = 8 * WX, PY = 4 * WY, THREADS = 32 * CTAW;
+};
+
+template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH, bool SKIP, int MINW, int CTAW = 8, int CTAWX = (CTAW < 4 ? CTAW : 4)>
+__global__ void __launch_bounds__(32 * CTAW, MINW / CTAW)
 march_texpair_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ MarchArgs args)
 {
+    typedef CtaShape<CTAW, CTAWX> S;
     extern __shared__ uint32_t s_mask[];
     if (SKIP) {                                                          // stage the empty-cell bit map (a few KB)
-        for (int i = threadIdx.x; i < args.cell_words; i += 256) s_mask[i] = __ldg(args.cell_bits + i);
+        for (int i = threadIdx.x; i < args.cell_words; i += S::THREADS) s_mask[i] = __ldg(args.cell_bits + i);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int lrow = fc.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int px = blockIdx.x * S::PX + (warp % S::WX) * 8 + (lane & 7);
+    const int lrow = fc.row0 + blockIdx.y * S::PY + (warp / S::WX) * 4 + (lane >> 3);
     const int py = owned_row_to_global(fc, lrow);
     if (px < fc.W && lrow < args.local_rows && py < fc.H) {
         const RaySetup r = setup_ray(fc, px, py);
@@ -554,18 +561,19 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
     while (pass()) {}
 }
 
-template <int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH, bool SKIP, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH, bool SKIP, int MINW, int CTAW = 8, int CTAWX = (CTAW < 4 ? CTAW : 4)>
+__global__ void __launch_bounds__(32 * CTAW, MINW / CTAW)
 march_nearest_kernel(const __grid_constant__ FrameConsts fc, const __grid_constant__ MarchArgs args)
 {
+    typedef CtaShape<CTAW, CTAWX> S;
     extern __shared__ uint32_t s_mask[];
     if (SKIP) {
-        for (int i = threadIdx.x; i < args.cell_words; i += 256) s_mask[i] = __ldg(args.cell_bits + i);
+        for (int i = threadIdx.x; i < args.cell_words; i += S::THREADS) s_mask[i] = __ldg(args.cell_bits + i);
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int lrow = fc.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int px = blockIdx.x * S::PX + (warp % S::WX) * 8 + (lane & 7);
+    const int lrow = fc.row0 + blockIdx.y * S::PY + (warp / S::WX) * 4 + (lane >> 3);
     const int py = owned_row_to_global(fc, lrow);
     if (px < fc.W && lrow < args.local_rows && py < fc.H) {
         const RaySetup r = setup_ray(fc, px, py);

@@ -67,6 +67,16 @@ struct DevBuf {
 // pipeline depth / resident CTAs per SM of the optimised kernels, measured on the headline frame
 // (lab r2: depth 4 at 64 registers / 4 CTAs per SM is the best choice across cameras, partitions, volume
 // shapes; the skipping forms carry the leap state and want the same register budget)
+// CTA shape (lab r2): 4 warps covering 16 x 8 pixels.  Against the 8-warp 32 x 8 shape: -2 % on the full headline
+// frame, -4 % at K0, -8 % on a 1/8 partition (a CTA lives as long as its slowest warp: smaller CTAs return their
+// registers sooner and fill the tail of a small grid at a finer grain); flatter 32 x 4 tiles lose 13 % at the oblique
+// camera K1 (texture-cache locality wants square tiles), single-warp CTAs lose everywhere.
+#ifndef VR_CTA_WARPS
+#define VR_CTA_WARPS 4
+#endif
+#ifndef VR_CTA_WX
+#define VR_CTA_WX 2
+#endif
 #ifndef VR_TP_DEPTH
 #define VR_TP_DEPTH 4
 #endif
@@ -413,7 +423,7 @@ template <typename T, int FORM, bool SKIP>
 void launch_texpair_form(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_TP_SKIP_DEPTH : VR_TP_DEPTH, SKIP, SKIP ? VR_TP_SKIP_MINB : VR_TP_MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_TP_SKIP_DEPTH : VR_TP_DEPTH, SKIP, 8 * (SKIP ? VR_TP_SKIP_MINB : VR_TP_MINB), VR_CTA_WARPS, VR_CTA_WX><<<grid, 32 * VR_CTA_WARPS, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
     if constexpr (FORM >= FORM_GENERAL) {
         if (plan.shape == SHAPE_MARK) VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); else VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false);
     } else {
@@ -441,7 +451,7 @@ template <int FORM, bool SKIP>
 void launch_nearest_form(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
 {
     using namespace vr;
-#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_nearest_kernel<TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_NN_SKIP_DEPTH : VR_NN_DEPTH, SKIP, SKIP ? VR_NN_SKIP_MINB : (FORM >= vr::FORM_GENERAL ? 5 : VR_NN_MINB)><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_nearest_kernel<TCDIV, WIN, UNIT, NOCAP, FORM, SKIP ? VR_NN_SKIP_DEPTH : VR_NN_DEPTH, SKIP, 8 * (SKIP ? VR_NN_SKIP_MINB : (FORM >= vr::FORM_GENERAL ? 5 : VR_NN_MINB)), VR_CTA_WARPS, VR_CTA_WX><<<grid, 32 * VR_CTA_WARPS, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
     if constexpr (FORM >= FORM_GENERAL) {
         if (plan.shape == SHAPE_MARK) VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); else VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, false);
     } else {
@@ -492,11 +502,14 @@ void launch_nearest_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid,
 #ifdef VR_LAB
 // development builds only (tools/lab/build_lab.sh): pipeline depth / occupancy variants of the DVR form, chosen per
 // launch through the environment: VR_LAB_TP="depth,minb"; returns -1 when the frame / variant is not covered
-template <typename T, int DEPTH, int MINB, bool SKIP>
-int lab_tp(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
+template <typename T, int DEPTH, int MINW, bool SKIP, int CTAW, int WX = (CTAW < 4 ? CTAW : 4)>
+int lab_tp(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s)
 {
     using namespace vr;
-#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
+    typedef CtaShape<CTAW, WX> S;
+    const dim3 grid((W + S::PX - 1) / S::PX, (row_end - row0 + S::PY - 1) / S::PY);
+    MarchArgs b = a; b.grid_ctas = grid.x * grid.y;
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINW, CTAW, WX><<<grid, S::THREADS, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, b)
     if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
     if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
     if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
@@ -504,61 +517,42 @@ int lab_tp(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream
     return -1;
 }
 template <typename T, bool SKIP>
-int lab_tp_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int depth, int minb)
+int lab_tp_s(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int depth, int minb, int ctaw)
 {
-    const int key = depth * 10 + minb;
+    // minb = resident warps per SM (register budget), ctaw = warps per CTA
+    const int key = depth * 10000 + minb * 100 + ctaw;
     switch (key) {
-        case 26: return lab_tp<T, 2, 6, SKIP>(plan, a, grid, s);
-        case 25: return lab_tp<T, 2, 5, SKIP>(plan, a, grid, s);
-        case 24: return lab_tp<T, 2, 4, SKIP>(plan, a, grid, s);
-        case 36: return lab_tp<T, 3, 6, SKIP>(plan, a, grid, s);
-        case 35: return lab_tp<T, 3, 5, SKIP>(plan, a, grid, s);
-        case 34: return lab_tp<T, 3, 4, SKIP>(plan, a, grid, s);
-        case 45: return lab_tp<T, 4, 5, SKIP>(plan, a, grid, s);
-        case 44: return lab_tp<T, 4, 4, SKIP>(plan, a, grid, s);
+        case 24808: return lab_tp<T, 2, 48, SKIP, 8>(plan, a, W, row0, row_end, s);
+        case 33208: return lab_tp<T, 3, 32, SKIP, 8>(plan, a, W, row0, row_end, s);
+        case 34008: return lab_tp<T, 3, 40, SKIP, 8>(plan, a, W, row0, row_end, s);
+        case 43208: return lab_tp<T, 4, 32, SKIP, 8>(plan, a, W, row0, row_end, s);
+        case 43204: return lab_tp<T, 4, 32, SKIP, 4>(plan, a, W, row0, row_end, s);
+        case 43202: return lab_tp<T, 4, 32, SKIP, 2>(plan, a, W, row0, row_end, s);
+        case 43201: return lab_tp<T, 4, 32, SKIP, 1>(plan, a, W, row0, row_end, s);
+        case 33604: return lab_tp<T, 3, 36, SKIP, 4>(plan, a, W, row0, row_end, s);
+        case 33602: return lab_tp<T, 3, 36, SKIP, 2>(plan, a, W, row0, row_end, s);
+        case 43604: return lab_tp<T, 4, 36, SKIP, 4>(plan, a, W, row0, row_end, s);
+        case 43602: return lab_tp<T, 4, 36, SKIP, 2>(plan, a, W, row0, row_end, s);
+        case 34004: return lab_tp<T, 3, 40, SKIP, 4>(plan, a, W, row0, row_end, s);
+        case 34002: return lab_tp<T, 3, 40, SKIP, 2>(plan, a, W, row0, row_end, s);
+        // squarer tiles: ctaw code 42 = 4 warps as 16x8 px, 21 = 2 warps as 8x8, 82 = 8 warps as 16x16, 41 = 4 warps as 8x16
+        case 43242: return lab_tp<T, 4, 32, SKIP, 4, 2>(plan, a, W, row0, row_end, s);
+        case 43221: return lab_tp<T, 4, 32, SKIP, 2, 1>(plan, a, W, row0, row_end, s);
+        case 43282: return lab_tp<T, 4, 32, SKIP, 8, 2>(plan, a, W, row0, row_end, s);
+        case 43241: return lab_tp<T, 4, 32, SKIP, 4, 1>(plan, a, W, row0, row_end, s);
+        case 33642: return lab_tp<T, 3, 36, SKIP, 4, 2>(plan, a, W, row0, row_end, s);
         default: return -1;
     }
 }
-template <int DEPTH, int MINB, bool SKIP>
-int lab_nn(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
-{
-    using namespace vr;
-#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_nearest_kernel<TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINB><<<grid, 256, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, a)
-    if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
-    if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
-    if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
-#undef VR_K
-    return -1;
-}
-template <bool SKIP>
-int lab_nn_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int depth, int minb)
-{
-    switch (depth * 10 + minb) {
-        case 28: return lab_nn<2, 8, SKIP>(plan, a, grid, s);
-        case 26: return lab_nn<2, 6, SKIP>(plan, a, grid, s);
-        case 25: return lab_nn<2, 5, SKIP>(plan, a, grid, s);
-        case 24: return lab_nn<2, 4, SKIP>(plan, a, grid, s);
-        case 38: return lab_nn<3, 8, SKIP>(plan, a, grid, s);
-        case 36: return lab_nn<3, 6, SKIP>(plan, a, grid, s);
-        case 35: return lab_nn<3, 5, SKIP>(plan, a, grid, s);
-        case 46: return lab_nn<4, 6, SKIP>(plan, a, grid, s);
-        default: return -1;
-    }
-}
-int lab_launch_nearest(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s)
-{
-    const char* e = std::getenv("VR_LAB_NN");
-    int depth = 0, minb = 0;
-    if (!e || std::sscanf(e, "%d,%d", &depth, &minb) != 2 || plan.form != vr::FORM_DVR) return -1;
-    return plan.skip ? lab_nn_s<true>(plan, a, grid, s, depth, minb) : lab_nn_s<false>(plan, a, grid, s, depth, minb);
-}
-int lab_launch_texpair(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid, cudaStream_t s, int bpv)
+int lab_launch_texpair(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int bpv)
 {
     const char* e = std::getenv("VR_LAB_TP");
-    int depth = 0, minb = 0;
-    if (!e || std::sscanf(e, "%d,%d", &depth, &minb) != 2 || plan.form != vr::FORM_DVR) return -1;
-    if (bpv == 2) return plan.skip ? lab_tp_s<uint16_t, true>(plan, a, grid, s, depth, minb) : lab_tp_s<uint16_t, false>(plan, a, grid, s, depth, minb);
-    return plan.skip ? lab_tp_s<uint8_t, true>(plan, a, grid, s, depth, minb) : lab_tp_s<uint8_t, false>(plan, a, grid, s, depth, minb);
+    int depth = 0, minb = 0, ctaw = 8;
+    if (!e || std::sscanf(e, "%d,%d,%d", &depth, &minb, &ctaw) < 2 || plan.form != vr::FORM_DVR) return -1;
+    if (bpv == 2) return plan.skip ? lab_tp_s<uint16_t, true>(plan, a, W, row0, row_end, s, depth, minb, ctaw)
+                                   : lab_tp_s<uint16_t, false>(plan, a, W, row0, row_end, s, depth, minb, ctaw);
+    return plan.skip ? lab_tp_s<uint8_t, true>(plan, a, W, row0, row_end, s, depth, minb, ctaw)
+                     : lab_tp_s<uint8_t, false>(plan, a, W, row0, row_end, s, depth, minb, ctaw);
 }
 #endif
 
@@ -570,14 +564,16 @@ int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int ro
     if (signalled) *signalled = false;
     if (row_end <= row0) return VR_OK;                      // this rank owns no row of the band (tiles < world)
     plan.fc.row0 = row0;
-    const dim3 grid((c->W + 31) / 32, (row_end - row0 + 7) / 8);
     if (plan.kernel == VR_KERNEL_DIRECT) {
+        const dim3 grid((c->W + vr::DIRECT_BLOCK_W - 1) / vr::DIRECT_BLOCK_W, (row_end - row0 + vr::DIRECT_BLOCK_H - 1) / vr::DIRECT_BLOCK_H);
         vr::DirectArgs args{};
         args.vol = c->d_vol; args.pitch = c->pitch; args.slice = c->slice;
         args.tf_lut = c->d_lut; args.out = d_out; args.local_rows = row_end;
         return c->bpv == 1 ? launch_direct_t<uint8_t, false>(c, plan, args, grid, s)
                            : launch_direct_t<uint16_t, false>(c, plan, args, grid, s);
     }
+    typedef vr::CtaShape<VR_CTA_WARPS, VR_CTA_WX> Shape;
+    const dim3 grid((c->W + Shape::PX - 1) / Shape::PX, (row_end - row0 + Shape::PY - 1) / Shape::PY);
     vr::MarchArgs a{};
     a.out = d_out; a.local_rows = row_end;
     a.tf_lut = plan.lut_final ? c->d_lut + 256 : c->d_lut;
@@ -589,15 +585,12 @@ int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int ro
     if (plan.kernel == VR_KERNEL_TEXPAIR_PIPE) {
         a.tex = c->tex2;
 #ifdef VR_LAB
-        if (lab_launch_texpair(plan, a, grid, s, c->bpv) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
+        if (lab_launch_texpair(plan, a, c->W, row0, row_end, s, c->bpv) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
 #endif
         if (c->bpv == 2) { if (plan.skip) launch_texpair_ts<uint16_t, true>(plan, a, grid, s); else launch_texpair_ts<uint16_t, false>(plan, a, grid, s); }
         else             { if (plan.skip) launch_texpair_ts<uint8_t, true>(plan, a, grid, s);  else launch_texpair_ts<uint8_t, false>(plan, a, grid, s); }
     } else {
         a.tex = c->tex;
-#ifdef VR_LAB
-        if (lab_launch_nearest(plan, a, grid, s) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
-#endif
         if (plan.skip) launch_nearest_s<true>(plan, a, grid, s); else launch_nearest_s<false>(plan, a, grid, s);
     }
     VR_CUDA(cudaGetLastError());
@@ -1047,18 +1040,22 @@ static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats
         if (e == cudaSuccess) rc = launch_march(c, plan, c->d_frame, t0 * T, t1 * T, bs, nullptr, nullptr);
         ++launches;
         if (e == cudaSuccess) e = cudaEventRecord(c->band_kdone[b], bs);
-        for (int lt = t0; lt < t1 && e == cudaSuccess; ++lt) {
-            const int y0 = (lt * c->world + c->rank) * T, rows = std::min(T, c->H - y0);
-            // consecutive local tiles are consecutive image rows when the frame is not partitioned: one copy per band
-            if (c->world == 1) {
-                const int y1 = std::min(c->H, t1 * T);
-                e = cudaMemcpyAsync(host_rgba + (size_t)y0 * row_floats, c->d_frame + (size_t)lt * T * row_floats,
-                                    (size_t)(y1 - y0) * row_floats * sizeof(float), cudaMemcpyDeviceToHost, bs);
-                break;
+        // The band's tiles are T*W*16-byte chunks, contiguous in the compact device image and world*T rows apart in
+        // the host frame: ONE strided 2-D copy per band (plus one plain copy if the frame ends in a partial tile).
+        {
+            const size_t tile_bytes = (size_t)T * row_floats * sizeof(float);
+            int full = 0;
+            for (int lt = t0; lt < t1; ++lt) if ((lt * c->world + c->rank) * T + T <= c->H) ++full;
+            if (full > 0 && e == cudaSuccess)
+                e = cudaMemcpy2DAsync(host_rgba + (size_t)(t0 * c->world + c->rank) * T * row_floats, tile_bytes * (size_t)c->world,
+                                      c->d_frame + (size_t)t0 * T * row_floats, tile_bytes, tile_bytes, (size_t)full,
+                                      cudaMemcpyDeviceToHost, bs);
+            for (int lt = t0 + full; lt < t1 && e == cudaSuccess; ++lt) {
+                const int y0 = (lt * c->world + c->rank) * T, rows = std::min(T, c->H - y0);
+                if (rows > 0)
+                    e = cudaMemcpyAsync(host_rgba + (size_t)y0 * row_floats, c->d_frame + (size_t)lt * T * row_floats,
+                                        (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, bs);
             }
-            if (rows > 0)
-                e = cudaMemcpyAsync(host_rgba + (size_t)y0 * row_floats, c->d_frame + (size_t)lt * T * row_floats,
-                                    (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, bs);
         }
         if (e == cudaSuccess) e = cudaEventRecord(c->band_cdone[b], bs);
         nb = b + 1;
