@@ -496,8 +496,9 @@ def run_ours(args):
         roof["samples_per_launch"] = counted["samples"]
         roof["rays_hit"] = counted["rays_hit"]
         roof["gsamples_per_s"] = counted["samples"] / (avg_kernel_ms * 1e-3) / 1e9
-    roof["traffic"] = ncu_traffic(cfg["key"], roof["kernel"])
-    roof["workload_key"] = cfg["key"]
+    wkey = cfg["key"] + ("/skip" if used[1] else "")
+    roof["traffic"] = ncu_traffic(wkey, roof["kernel"])
+    roof["workload_key"] = wkey
 
     # the same frame without early-ray termination: every ray marches through the whole box
     dense = None

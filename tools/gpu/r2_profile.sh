@@ -27,9 +27,9 @@ cap texpair_C4_K2      march_texpair_kernel "C4/K2/trilinear/0.02/0-4095"
 cap texpair_C4_K0      march_texpair_kernel "C4/K0/trilinear/0.02/0-4095" --camera K0
 cap texpair_C4_alpha1  march_texpair_kernel "C4/K2/trilinear/1.0/0-4095" --alpha 1.0
 cap nearest_C4_K2      march_nearest_kernel "C4/K2/nearest/0.02/0-4095" --filter nearest
-cap texpair_C4_window_skip march_texpair_kernel "C4/K2/trilinear/0.05/1000-3000" --window 1000 3000 --alpha 0.05
-cap texpair_C3_skip    march_texpair_kernel "C3/K2/trilinear/0.05/1000-3000" --config C3 --alpha 0.05
+cap texpair_C4_window_skip march_texpair_kernel "C4/K2/trilinear/0.05/1000-3000/skip" --window 1000 3000 --alpha 0.05
+cap texpair_C3_skip    march_texpair_kernel "C3/K2/trilinear/0.05/1000-3000/skip" --config C3 --alpha 0.05
 cap texpair_C2         march_texpair_kernel "C2/K2/trilinear/0.02/0-255" --config C2
 cap texpair_C5         march_texpair_kernel "C5/K2/trilinear/0.02/0-4095" --config C5
 ls -la $O | head -40
-cuobjdump -sass -fun $(cuobjdump -elf volume-renderer_b200/lib/libvolren_b200.so | grep -o "_ZN2vr20march_texpair_kernelItLi0ELi1ELb1ELb1ELi0ELi4ELb0ELi4EEEvNS_11FrameConstsENS_9MarchArgsE" | head -1) volume-renderer_b200/lib/libvolren_b200.so > $O/sass_texpair_headline.txt 2>&1
+cuobjdump -sass -fun $(cuobjdump -elf volume-renderer_b200/lib/libvolren_b200.so | grep -o "_ZN2vr20march_texpair_kernelItLi0ELi1ELb1ELb1ELi0ELi4ELb0ELi32ELi4ELi2EEEvNS_11FrameConstsENS_9MarchArgsE" | head -1) volume-renderer_b200/lib/libvolren_b200.so > $O/sass_texpair_headline.txt 2>&1
