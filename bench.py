@@ -374,7 +374,7 @@ def run_ours(args):
         for creating in (True, False):                            # rank 0 creates, barrier, the others attach
             try:
                 if creating == (rank == 0):
-                    shared = vdist.SharedHostFrame(name, W, H, rank, world, create=creating)
+                    shared = vdist.SharedHostFrame(name, W, H, rank, world, create=creating, buffers=2)
             except Exception as e:
                 ok = 0
                 print(f"bench.py: rank {rank}: shared host frame unavailable ({e}); rank 0 reads the frame back alone", file=sys.stderr)
@@ -387,7 +387,7 @@ def run_ours(args):
                 shared.close()
             shared = None
     e2e_mode = "single GPU: vr_render (row bands overlap the device->host copy)" if world == 1 else \
-               ("every rank copies its own row tiles into one shared page-locked host frame" if shared is not None
+               ("every rank copies its own row tiles (banded, overlapping its march) into a shared page-locked host frame, two frames in flight" if shared is not None
                 else "hand-off to rank 0 on the device, rank 0 copies the frame to the host")
     barrier()
     t0 = time.perf_counter()
@@ -400,8 +400,9 @@ def run_ours(args):
         if world == 1:
             ctx.render_to_host_ptr(pinned.data_ptr())
         elif shared is not None:
-            shared.wait_released(i)                                   # the consumer is done with the previous frame
-            ctx.render_owned_to_host_ptr(shared.frame_ptr)
+            # two host frames: a rank may start frame i+1 while the consumer still waits for the slowest rank of frame i
+            shared.wait_writable(i + 1)                               # the buffer's previous frame (i - 1) has been consumed
+            ctx.render_owned_to_host_ptr(shared.buffer_ptr(i + 1))
             shared.mark_done(i + 1)
             if rank == 0:
                 shared.wait_all_done(i + 1)                           # the whole frame is in host memory
@@ -452,7 +453,9 @@ def run_ours(args):
             torch.cuda.synchronize()
             same_as_single = bool(torch.equal(multi.view(torch.int32), single.view(torch.int32)))
             if shared is not None:
-                host_same = bool(np.array_equal(shared.frame.view(np.uint32), single.cpu().numpy().view(np.uint32)))
+                last = args.warmup + args.steps                      # the last frame the e2e loop produced
+                host_same = bool(np.array_equal(shared.buffer_of(last).view(np.uint32), single.cpu().numpy().view(np.uint32))
+                                 and np.array_equal(shared.buffer_of(last - 1).view(np.uint32), single.cpu().numpy().view(np.uint32)))
             ctx.set_partition(rank, world, TILE_ROWS)
         barrier()
 

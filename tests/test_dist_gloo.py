@@ -81,32 +81,34 @@ def test_partition_maps_are_a_bijection():
                 assert max(counts) - min(counts) <= tile_rows
 
 
-def _shared_frame_worker(rank, world, name, tile_rows, H, W, frames, out_path):
+def _shared_frame_worker(rank, world, name, tile_rows, H, W, frames, out_path, buffers=1):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python")]
     from volren_b200 import dist as vdist
     import time
     if rank != 0:
         for _ in range(200):                       # wait for rank 0 to create the segment
             try:
-                sf = vdist.SharedHostFrame(name, W, H, rank, world, create=False, register_cuda=False)
+                sf = vdist.SharedHostFrame(name, W, H, rank, world, create=False, register_cuda=False, buffers=buffers)
                 break
             except FileNotFoundError:
                 time.sleep(0.02)
     else:
-        sf = vdist.SharedHostFrame(name, W, H, rank, world, create=True, register_cuda=False)
+        sf = vdist.SharedHostFrame(name, W, H, rank, world, create=True, register_cuda=False, buffers=buffers)
     ok = 1
     tiles = (H + tile_rows - 1) // tile_rows
     for f in range(1, frames + 1):
-        sf.wait_released(f - 1)                    # never overwrite a frame the consumer still reads
+        sf.wait_writable(f)                        # never overwrite a frame the consumer still reads
+        if rank == 1 and f == 2:
+            time.sleep(0.05)                       # a straggler: with two buffers the others run one frame ahead
         for t in range(rank, tiles, world):
             y0, y1 = t * tile_rows, min((t + 1) * tile_rows, H)
             ys = np.arange(y0, y1, dtype=np.float32)[:, None, None]
-            sf.frame[y0:y1] = ys * 1000.0 + f      # value encodes (row, frame)
+            sf.buffer_of(f)[y0:y1] = ys * 1000.0 + f      # value encodes (row, frame)
         sf.mark_done(f)
         if rank == 0:
             sf.wait_all_done(f)
             expect = np.arange(H, dtype=np.float32)[:, None, None] * 1000.0 + f
-            if not np.array_equal(sf.frame, np.broadcast_to(expect, (H, W, 4))):
+            if not np.array_equal(sf.buffer_of(f), np.broadcast_to(expect, (H, W, 4))):
                 ok = 0
             sf.release(f)
     if rank == 0:
@@ -115,12 +117,13 @@ def _shared_frame_worker(rank, world, name, tile_rows, H, W, frames, out_path):
     sf.close()
 
 
+@pytest.mark.parametrize("buffers", [1, 2])
 @pytest.mark.parametrize("world,tile_rows,H", [(2, 16, 70), (3, 4, 50)])
-def test_shared_host_frame_protocol(tmp_path, world, tile_rows, H):
+def test_shared_host_frame_protocol(tmp_path, world, tile_rows, H, buffers):
     """The multi-GPU end-to-end hand-off on the host: every rank writes its row tiles into one shared
     frame; done/released flags order completion and reuse without any collective (CPU only: the
     device->host copies of vr_render_owned_to_host are replaced by numpy stores)."""
     out = str(tmp_path / "ok.npy")
-    name = f"volren_test_{os.getpid()}_{world}"
-    mp.spawn(_shared_frame_worker, args=(world, name, tile_rows, H, 24, 5, out), nprocs=world, join=True)
+    name = f"volren_test_{os.getpid()}_{world}_{buffers}"
+    mp.spawn(_shared_frame_worker, args=(world, name, tile_rows, H, 24, 6, out, buffers), nprocs=world, join=True)
     assert np.load(out)[0] == 1

@@ -83,18 +83,22 @@ def assemble_reference(gathered: torch.Tensor, height: int, tile_rows: int) -> t
 
 
 class SharedHostFrame:
-    """One W x H RGBA32F frame in POSIX shared memory, mapped by every rank process (one process per
+    """`buffers` W x H RGBA32F frames in POSIX shared memory, mapped by every rank process (one process per
     GPU) and page-locked in each with cudaHostRegister, so that every rank copies its own row tiles
     device->host over its own PCIe link (vr_render_owned_to_host).  Two tiny flag arrays in the same
     segment order the hand-off without any collective: done[r] = last frame rank r has fully written,
     released = last frame the consumer (rank 0) is finished with.  x86 total store order + the stream
-    synchronisation inside vr_render_owned_to_host make plain stores sufficient."""
+    synchronisation inside vr_render_owned_to_host make plain stores sufficient.
+    Frame f (1, 2, ...) lives in buffer f % buffers.  With two buffers the producers may run one frame ahead of
+    the consumer: a rank starts frame f as soon as frame f - buffers has been released, instead of waiting for
+    the slowest rank and the consumer after every frame."""
 
     HEADER = 4096       # bytes: int64 done[world] at 0, int64 released at 2048
 
-    def __init__(self, name: str, width: int, height: int, rank: int, world: int, create: bool, register_cuda: bool = True):
-        self.rank, self.world, self.W, self.H = rank, world, width, height
-        nbytes = self.HEADER + width * height * 16
+    def __init__(self, name: str, width: int, height: int, rank: int, world: int, create: bool, register_cuda: bool = True,
+                 buffers: int = 1):
+        self.rank, self.world, self.W, self.H, self.buffers = rank, world, width, height, buffers
+        nbytes = self.HEADER + buffers * width * height * 16
         if create:
             # a tmpfs that is too small lets shm_open/ftruncate/mmap succeed and then kills the process with
             # SIGBUS on first touch: refuse up front (the caller falls back to rank 0 reading the frame back)
@@ -117,13 +121,14 @@ class SharedHostFrame:
         buf = np.ndarray((nbytes,), dtype=np.uint8, buffer=self.shm.buf)
         self.done = buf[:8 * world].view(np.int64)
         self.released = buf[2048:2056].view(np.int64)
-        self.frame = buf[self.HEADER:].view(np.float32).reshape(height, width, 4)
+        self.frames = buf[self.HEADER:].view(np.float32).reshape(buffers, height, width, 4)
+        self.frame = self.frames[0]
         if create:
             self.done[:] = 0
             self.released[:] = 0
         self.registered = False
         if register_cuda:
-            rc = torch.cuda.cudart().cudaHostRegister(self.frame.ctypes.data, width * height * 16, 0)
+            rc = torch.cuda.cudart().cudaHostRegister(self.frames.ctypes.data, buffers * width * height * 16, 0)
             if int(rc) != 0:
                 raise RuntimeError(f"cudaHostRegister failed: {rc}")
             self.registered = True
@@ -131,6 +136,17 @@ class SharedHostFrame:
     @property
     def frame_ptr(self) -> int:
         return self.frame.ctypes.data
+
+    def buffer_of(self, frame_no: int) -> np.ndarray:
+        return self.frames[frame_no % self.buffers]
+
+    def buffer_ptr(self, frame_no: int) -> int:
+        return self.buffer_of(frame_no).ctypes.data
+
+    def wait_writable(self, frame_no: int, timeout_s: float = 10.0):
+        """Producer side, before writing frame `frame_no`: its buffer's previous occupant (frame_no - buffers) has
+        been released by the consumer."""
+        self.wait_released(frame_no - self.buffers, timeout_s)
 
     def wait_released(self, frame_no: int, timeout_s: float = 10.0):
         """Producer side: the consumer is finished with frame `frame_no` (the buffer may be overwritten)."""
@@ -154,9 +170,9 @@ class SharedHostFrame:
 
     def close(self):
         if self.registered:
-            torch.cuda.cudart().cudaHostUnregister(self.frame.ctypes.data)
+            torch.cuda.cudart().cudaHostUnregister(self.frames.ctypes.data)
             self.registered = False
-        self.done = self.released = self.frame = None
+        self.done = self.released = self.frame = self.frames = None
         try:
             self.shm.close()
             if self.created:
