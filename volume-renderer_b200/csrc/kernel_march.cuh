@@ -52,6 +52,7 @@ struct MarchArgs {
     // empty-cell bit map (SKIP forms): bit (cz*cell_ny + cy)*cell_nx + cx, c = (base voxel index + 1) >> cell_shift
     const uint32_t* cell_bits;
     int cell_words, cell_shift, cell_nx, cell_nxy;
+    int skip_check_mask;         // checkpoints every (mask + 1)-th pass of the unrolled loop (mask + 1 a power of two)
     // fused multi-GPU hand-off: the last CTA of the grid to finish publishes this rank's arrival in the
     // frame owner's barrier word (peer memory), replacing a one-thread kernel per frame
     unsigned int* done_counter;
@@ -288,7 +289,7 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, const M
 }
 
 // The same march with empty-space skipping (see the file header).  The pipelined loop is kept as it is; the cell
-// map is consulted only at CHECKPOINTS: the first sample and then every SKIP_CHECK_EVERY-th pass of the unrolled
+// map is consulted only at CHECKPOINTS: the first sample and then every (skip_check_mask+1)-th pass of the unrolled
 // loop -- a WARP-UNIFORM condition, so lanes never wait for each other's checkpoints.  At a checkpoint `examine`
 // looks at the front sample's cell.  Non-empty: carry on.  Empty: leap -- the number of further samples certain to
 // stay in the cell (a LOWER bound, 0.05 voxel inside the cell and the box) is skipped by performing exactly that
@@ -296,7 +297,6 @@ __device__ __forceinline__ void march_ray_texpair(const FrameConsts& fc, const M
 // until a non-empty cell or the end of the box.  Skipped samples never enter the ring; they contribute exactly 0,
 // so consuming the ring in order reproduces the reference's accumulation sequence.  (Samples of an empty cell
 // met between two checkpoints are simply processed: always exact, only slower.)
-constexpr int SKIP_CHECK_EVERY = 4;
 
 template <typename T, int TCDIV, int WIN, bool UNIT, bool NOCAP, int FORM, int DEPTH>
 __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, const MarchArgs& args, const uint32_t* __restrict__ s_mask,
@@ -363,7 +363,7 @@ __device__ __forceinline__ void march_ray_texpair_skip(const FrameConsts& fc, co
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             advance();
-            key[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
+            key[fill] = front(F[fill], k == 0 && (it & args.skip_check_mask) == 0);
             consume_pair<T, WIN, FORM>(fc, args, F[k], C, A);
             if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
         }
@@ -551,7 +551,7 @@ __device__ __forceinline__ void march_ray_nearest_skip(const FrameConsts& fc, co
         for (int k = 0; k < DEPTH; ++k) {
             const int fill = (k + DEPTH - 1) % DEPTH, next = (k + 1) % DEPTH;
             advance();
-            key[fill] = front(F[fill], k == 0 && (it & (SKIP_CHECK_EVERY - 1)) == 0);
+            key[fill] = front(F[fill], k == 0 && (it & args.skip_check_mask) == 0);
             consume(F[k]);
             if (key[next] > 0x3F800000u || __float_as_uint(A) >= 0x3F733333u) return false;
         }
