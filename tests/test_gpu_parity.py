@@ -389,6 +389,36 @@ def test_odd_image_sizes_and_banded_frames(W, H):
         compare(img, ref, f"{W}x{H} filter {filt}")
 
 
+def test_launch_order_table_follows_camera_partition_and_bands():
+    """The march kernels start their CTA tiles longest rays first, from a table the GPU rebuilds whenever the camera,
+    the box, the partition or the band changes (cta_order_kernel).  One context, a moving camera, changing partitions,
+    device frames and banded host frames: every frame must stay bit-identical to the generic loop's (which never uses
+    the table) -- a stale or incomplete table would leave tiles of an earlier frame behind."""
+    vox, dims, bpv, vs = scenarios.volume("mix_64x64x32_u16")
+    W, H = 1280, 724                                   # large enough for the banded host path
+    cams = [scenarios.camera(k) for k in ("K0", "K1", "K2", "K1", "inside", "K0")]
+    with vb.Context(W, H) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        for i, cam in enumerate(cams):
+            filt = i & 1
+            kw = dict(alpha_scale=0.05 + 0.01 * i, min_val=0, max_val=4095, filter=filt)
+            world = (1, 2, 3, 1, 8, 1)[i]
+            for rank in sorted({0, world - 1}):
+                ctx.set_partition(rank, world, 8)
+                ctx.set_camera(cam)
+                ctx.set_params(vb.default_params(kernel=vb.KERNEL_DIRECT, **kw))
+                ref, st = ctx.render()
+                assert st.kernel_used == vb.KERNEL_DIRECT
+                ctx.set_params(vb.default_params(**kw))
+                img, st = ctx.render()                 # banded host frame: one table per band
+                assert st.kernel_used == expected_kernel(kw)
+                assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), f"host frame {i} rank {rank}/{world}"
+                ctx.render_device(0)                   # whole partition in one launch: another table
+                dev = ctx.read_frame()
+                owned = ((np.arange(H) // 8) % world) == rank      # rows of other ranks keep whatever earlier frames left
+                assert np.array_equal(dev[owned].view(np.uint32), ref[owned].view(np.uint32)), f"device frame {i} rank {rank}/{world}"
+
+
 # ---------------------------------------------------------------- ingest
 
 def test_volume_stats_match_reference_loops():

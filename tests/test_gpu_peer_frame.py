@@ -118,6 +118,7 @@ def _worker_device_barrier(rank, world, port, out_path, fused=False):
                           f"status {ctx.peer_frame_status(ptr)}", flush=True)
                 ctx.peer_frame_release(ptr, f, is_owner=True)
         if rank == 0:
+            torch.cuda.synchronize(dev)      # the last release is a kernel in the context's (non-blocking) stream; the status read is not ordered after it
             st = ctx.peer_frame_status(ptr)
             if st["timed_out"] or st["arrivals"] != frames * world or st["released"] != frames:
                 ok = 0

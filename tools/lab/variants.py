@@ -68,8 +68,11 @@ def main():
     off = dict(empty_skip=vb.SKIP_OFF)
     on = dict(empty_skip=vb.SKIP_ON)
     combos = ((4, 32, 8), (4, 32, 4), (4, 32, 42), (4, 32, 41), (4, 32, 82), (4, 32, 21), (4, 32, 2), (3, 36, 42))
+    if os.environ.get("LAB_COMBOS"):                       # e.g. LAB_COMBOS="4,32,42;4,24,42;3,24,42"
+        combos = tuple(tuple(int(v) for v in c.split(",")) for c in os.environ["LAB_COMBOS"].split(";"))
     tpv = [("default", None, off)] + [(f"d{d} w{w} cta{c}", f"{d},{w},{c}", off) for d, w, c in combos]
-    skv = [("skip default", None, on)] + [(f"skip d{d} w{w} cta{c}", f"{d},{w},{c}", on) for d, w, c in ((4, 32, 8), (4, 32, 4), (4, 32, 42), (4, 32, 82))]
+    skv = [("skip default", None, on)] + [(f"skip d{d} w{w} cta{c}", f"{d},{w},{c}", on) for d, w, c in
+                                          (combos if os.environ.get("LAB_COMBOS") else ((4, 32, 8), (4, 32, 4), (4, 32, 42), (4, 32, 82)))]
     n = 256 if quick else 1024
     with vb.Context(1920, 1080) as ctx:
         ctx.upload_synthetic((n, n, n), 2, 4095, workloads.SEEDS["C4"])

@@ -53,6 +53,10 @@ struct MarchArgs {
     const uint32_t* cell_bits;
     int cell_words, cell_shift, cell_nx, cell_nxy;
     int skip_check_mask;         // checkpoints every (mask + 1)-th pass of the unrolled loop (mask + 1 a power of two)
+    // launch order of the CTA tiles (small grids only; nullptr = row-major): entry b = tile (x | y << 16) taken by the
+    // b-th CTA the hardware starts.  The host sorts the tiles by the estimated length of their rays, longest first, so
+    // that what runs on the draining machine at the end of the grid are the short rays (LPT scheduling)
+    const uint32_t* cta_order;
     // fused multi-GPU hand-off: the last CTA of the grid to finish publishes this rank's arrival in the
     // frame owner's barrier word (peer memory), replacing a one-thread kernel per frame
     unsigned int* done_counter;
@@ -391,8 +395,10 @@ march_texpair_kernel(const __grid_constant__ FrameConsts fc, const __grid_consta
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * S::PX + (warp % S::WX) * 8 + (lane & 7);
-    const int lrow = fc.row0 + blockIdx.y * S::PY + (warp / S::WX) * 4 + (lane >> 3);
+    unsigned bx = blockIdx.x, by = blockIdx.y;
+    if (args.cta_order) { const unsigned t = __ldg(args.cta_order + blockIdx.y * gridDim.x + blockIdx.x); bx = t & 0xffffu; by = t >> 16; }
+    const int px = bx * S::PX + (warp % S::WX) * 8 + (lane & 7);
+    const int lrow = fc.row0 + by * S::PY + (warp / S::WX) * 4 + (lane >> 3);
     const int py = owned_row_to_global(fc, lrow);
     if (px < fc.W && lrow < args.local_rows && py < fc.H) {
         const RaySetup r = setup_ray(fc, px, py);
@@ -572,8 +578,10 @@ march_nearest_kernel(const __grid_constant__ FrameConsts fc, const __grid_consta
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = blockIdx.x * S::PX + (warp % S::WX) * 8 + (lane & 7);
-    const int lrow = fc.row0 + blockIdx.y * S::PY + (warp / S::WX) * 4 + (lane >> 3);
+    unsigned bx = blockIdx.x, by = blockIdx.y;
+    if (args.cta_order) { const unsigned t = __ldg(args.cta_order + blockIdx.y * gridDim.x + blockIdx.x); bx = t & 0xffffu; by = t >> 16; }
+    const int px = bx * S::PX + (warp % S::WX) * 8 + (lane & 7);
+    const int lrow = fc.row0 + by * S::PY + (warp / S::WX) * 4 + (lane >> 3);
     const int py = owned_row_to_global(fc, lrow);
     if (px < fc.W && lrow < args.local_rows && py < fc.H) {
         const RaySetup r = setup_ray(fc, px, py);

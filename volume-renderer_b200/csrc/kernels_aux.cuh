@@ -310,4 +310,66 @@ __global__ void popcount_kernel(const unsigned int* __restrict__ bits, uint64_t 
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// ---- launch order of the march kernels' CTA tiles: longest rays first ---------------------------------------------
+// One CTA.  Pass 1: every tile's cost = the longest chord of its centre and corner rays through the box (computeRay /
+// intersectRayAABB, VolumeRenderer.cs:194-238, evaluated approximately -- it only orders work), quantised into 1024
+// classes (class 0 = longest), histogram in shared memory.  Pass 2: exclusive scan of the classes.  Pass 3: scatter,
+// order[offset[class]++] = tile x | y << 16.  Every tile appears exactly once whatever the atomics' order.
+__device__ __forceinline__ float ray_chord(const FrameConsts& fc, float pxc, float pyc)
+{
+    const float* cam = fc.cam;
+    const float aspect = (float)fc.W / (float)fc.H;
+    const float x = aspect * (2.0f * pxc / (float)fc.W - 1.0f), y = 2.0f * pyc / (float)fc.H - 1.0f, z = -cam[20];
+    const float r0 = rsqrtf(x * x + y * y + z * z);
+    const float dx = x * r0, dy = y * r0, dz = z * r0;
+    float m[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m[i] = cam[i] * dx + cam[4 + i] * dy + cam[8 + i] * dz;
+    const float r1 = rsqrtf(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+    float t0 = -3.0e38f, t1 = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float inv = 1.0f / (m[i] * r1);
+        const float a = (fc.pmin[i] - cam[16 + i]) * inv, b = (fc.pmax[i] - cam[16 + i]) * inv;
+        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    }
+    const float len = t1 - fmaxf(t0, 0.0f);
+    return len > 0.0f ? len : 0.0f;                                     // NaN -> 0
+}
+
+__global__ void __launch_bounds__(1024)
+cta_order_kernel(const __grid_constant__ FrameConsts fc, int row0, int row_end, int px_w, int px_h, int gx, int gy,
+                 uint32_t* __restrict__ order, uint32_t* __restrict__ scratch)
+{
+    constexpr int CLASSES = 1024;
+    __shared__ unsigned int s_count[CLASSES];
+    const int n = gx * gy;
+    s_count[threadIdx.x] = 0u;
+    __syncthreads();
+    const float ex = fc.pmax[0] - fc.pmin[0], ey = fc.pmax[1] - fc.pmin[1], ez = fc.pmax[2] - fc.pmin[2];
+    const float scale = (float)(CLASSES - 1) * rsqrtf(ex * ex + ey * ey + ez * ez);     // chord <= diagonal
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int by = i / gx, bx = i - by * gx;
+        const int l0 = row0 + by * px_h, l1 = min(l0 + px_h, row_end) - 1;
+        const float y0 = (float)min(owned_row_to_global(fc, l0), fc.H - 1) + 0.5f, y1 = (float)min(owned_row_to_global(fc, l1), fc.H - 1) + 0.5f;
+        const float x0 = (float)(bx * px_w) + 0.5f, x1 = (float)min(bx * px_w + px_w, fc.W) - 0.5f;
+        const float c = fmaxf(fmaxf(fmaxf(ray_chord(fc, x0, y0), ray_chord(fc, x1, y0)), fmaxf(ray_chord(fc, x0, y1), ray_chord(fc, x1, y1))),
+                              ray_chord(fc, 0.5f * (x0 + x1), 0.5f * (y0 + y1)));
+        const int cls = CLASSES - 1 - min(max((int)(c * scale), 0), CLASSES - 1);
+        scratch[i] = (uint32_t)cls;
+        atomicAdd(&s_count[cls], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                              // exclusive scan, 1024 classes
+        unsigned int run = 0u;
+        for (int k = 0; k < CLASSES; ++k) { const unsigned int v = s_count[k]; s_count[k] = run; run += v; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int by = i / gx, bx = i - by * gx;
+        const unsigned int pos = atomicAdd(&s_count[scratch[i]], 1u);
+        order[pos] = (uint32_t)bx | ((uint32_t)by << 16);
+    }
+}
+
 }  // namespace vr
