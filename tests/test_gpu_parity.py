@@ -235,7 +235,10 @@ def test_skipping_is_refused_when_an_empty_sample_still_contributes():
         compare(img, ref, "negative min_val")
 
 
-@pytest.mark.parametrize("dims,bpv", [((40, 33, 20), 1), ((70, 17, 130), 2), ((8, 8, 8), 2), ((1, 1, 1), 1), ((300, 200, 9), 2)])
+@pytest.mark.parametrize("dims,bpv", [((40, 33, 20), 1), ((70, 17, 130), 2), ((8, 8, 8), 2), ((1, 1, 1), 1), ((300, 200, 9), 2),
+                                      # 16-byte aligned rows: the fused ingest kernel (padded copy + cell table in one read)
+                                      ((64, 40, 33), 2), ((128, 24, 20), 1), ((16, 9, 9), 1), ((8, 1, 1), 2), ((264, 31, 17), 2),
+                                      ((512, 512, 256), 1), ((1024, 130, 70), 2)])
 def test_cell_table_matches_numpy(dims, bpv):
     """Per-cell min/max (SURVEY 8f-2's brick table): cell c covers voxel indices [c*2^s - 1, (c+1)*2^s - 1] per axis."""
     rng = np.random.default_rng(5)
@@ -425,7 +428,8 @@ def test_volume_stats_match_reference_loops():
     """fused pad + min/max kernel and the histogram kernel vs a numpy restatement of RendererCore.cpp:360-405."""
     rng = np.random.default_rng(3)
     # (51, 41, 31): odd voxel count -> the scalar tail behind the 16-byte vector body; 65535: full u16 range
-    for bpv, hi, dims in ((1, 256, (50, 40, 30)), (2, 3000, (50, 40, 30)), (1, 256, (51, 41, 31)), (2, 65536, (51, 41, 31))):
+    for bpv, hi, dims in ((1, 256, (50, 40, 30)), (2, 3000, (50, 40, 30)), (1, 256, (51, 41, 31)), (2, 65536, (51, 41, 31)),
+                          (1, 256, (48, 40, 30)), (2, 3000, (48, 40, 30)), (2, 65536, (256, 9, 11))):     # aligned rows: fused ingest kernel
         vox = rng.integers(0 if bpv == 1 else 17, hi, dims[0] * dims[1] * dims[2]).astype(np.uint8 if bpv == 1 else np.uint16)
         with vb.Context(32, 32) as ctx:
             ctx.upload_volume(vox, dims)

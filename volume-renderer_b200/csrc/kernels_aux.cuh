@@ -40,6 +40,138 @@ __global__ void pad_minmax_kernel(const T* __restrict__ src, T* __restrict__ dst
     if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
 }
 
+// ---- ingest, fused: padded copy + per-cell min/max table + dataset min/max in ONE read of the source ---------------
+// Fast path of the upload (rows of the source 16-byte aligned: nx a multiple of 16 / sizeof(T)); HBM-bound: 16-byte loads
+// and 16-byte stores, no shared-memory staging of the data.  A warp per padded row, 8 rows (one 8-row group of one
+// padded slice) per CTA pass:
+//  * lane L loads source vector k = 32*i + L; padded vector k is the same data moved up by ONE element (padded index =
+//    voxel index + 1), the element shifted in comes from the lane below (__shfl_up; across the 32-vector boundary from
+//    lane 31 of the previous pass); vectors past the end of the row replicate the last voxel (GL_CLAMP_TO_EDGE);
+//  * the same registers feed the cell table: per aligned group of 8 voxels a SIMD min/max tree (__vminu2 / __vminu4), then
+//    one shared-memory atomic pair per group into the CTA's row of cells (all 8 rows of a group lie in the same band of
+//    cells because the cell side is a multiple of 8).  Padded index j = voxel + 1 belongs to cell j >> shift and, when j is
+//    a multiple of the cell side, also to the cell before it (a trilinear footprint based at j - 1 reaches it): handled
+//    along x per group (its last voxel), along y with a second row of cells for the group's first row, along z when the
+//    CTA's row of cells is flushed -- one global atomic pair per cell and CTA pass;
+//  * rows of the padding (jy or jz = 0, N+1) are copies of real rows and only written.
+// `gmin`/`gmax`: 32-bit cell tables (initialised to 0xffffffff / 0), converted to the 16-bit product tables -- together
+// with the dataset's min/max, which is the min/max over the cells -- by cell_table_finish_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad_cells_kernel(const T* __restrict__ src, T* __restrict__ dst, int nx, int ny, int nz, uint32_t pitch,
+                 int shift, int cnx, int cny, unsigned int* __restrict__ gmin, unsigned int* __restrict__ gmax)
+{
+    constexpr int PER = 16 / (int)sizeof(T), SH = 8 * (int)sizeof(T), G = PER / 8;
+    extern __shared__ unsigned int s_cells[];                       // [2 tables][lo | hi][cnx]
+    unsigned int* s_lo0 = s_cells, *s_hi0 = s_cells + cnx, *s_lo1 = s_cells + 2 * cnx, *s_hi1 = s_cells + 3 * cnx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, side = 1 << shift;
+    const int groups = (ny + 2 + 7) / 8;
+    const uint64_t passes = (uint64_t)groups * (uint64_t)(nz + 2);
+    const int nvs = nx / PER, nvd = (int)(pitch / PER);
+    for (uint64_t it = blockIdx.x; it < passes; it += gridDim.x) {
+        const int jz = (int)(it / (uint64_t)groups), jy0 = (int)(it - (uint64_t)jz * groups) * 8, jy = jy0 + warp;
+        const bool real_z = jz >= 1 && jz <= nz;
+        const bool two_bands = jy0 > 0 && (jy0 & (side - 1)) == 0;                   // the group's first row also belongs to the band before
+        if (real_z) {
+            for (int i = threadIdx.x; i < 2 * cnx; i += 256) { s_cells[i] = (i < cnx) ? 0xffffffffu : 0u; s_cells[2 * cnx + i] = (i < cnx) ? 0xffffffffu : 0u; }
+            __syncthreads();
+        }
+        if (jy <= ny + 1) {
+            const int y = min(max(jy - 1, 0), ny - 1), z = min(max(jz - 1, 0), nz - 1);
+            const T* s = src + ((uint64_t)z * ny + y) * (uint64_t)nx;
+            const uint4* sv = reinterpret_cast<const uint4*>(s);
+            uint4* dv = reinterpret_cast<uint4*>(dst + ((uint64_t)jz * (uint64_t)(ny + 2) + (uint64_t)jy) * (uint64_t)pitch);
+            const bool contrib = real_z && jy >= 1 && jy <= ny;
+            const bool extra = contrib && warp == 0 && two_bands;
+            const unsigned int last = (unsigned int)s[nx - 1];
+            unsigned int lastw = last | (last << SH); if (SH == 8) lastw |= lastw << 16;
+            unsigned int carry = (unsigned int)s[0];
+            uint4 nxt = make_uint4(lastw, lastw, lastw, lastw);
+            if (lane < nvs) nxt = __ldg(sv + lane);
+            for (int k0 = 0; k0 < nvd; k0 += 32) {
+                const int k = k0 + lane;
+                const bool has = k < nvs;
+                const uint4 own = nxt;                                                 // loaded one pass ahead
+                nxt = make_uint4(lastw, lastw, lastw, lastw);
+                if (k + 32 < nvs) nxt = __ldg(sv + k + 32);
+                const unsigned int own_last = own.w >> (32 - SH);
+                unsigned int prev_last = __shfl_up_sync(0xffffffffu, own_last, 1);
+                if (lane == 0) prev_last = carry;
+                carry = __shfl_sync(0xffffffffu, own_last, 31);
+                if (k < nvd) {
+                    uint4 o;
+                    o.x = (own.x << SH) | prev_last;
+                    o.y = __funnelshift_l(own.x, own.y, SH);
+                    o.z = __funnelshift_l(own.y, own.z, SH);
+                    o.w = __funnelshift_l(own.z, own.w, SH);
+                    dv[k] = o;
+                }
+                if (contrib && has) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        unsigned int lo, hi, tail;
+                        if (sizeof(T) == 2) {
+                            lo = __vminu2(__vminu2(own.x, own.y), __vminu2(own.z, own.w));
+                            hi = __vmaxu2(__vmaxu2(own.x, own.y), __vmaxu2(own.z, own.w));
+                            lo = min(lo & 0xffffu, lo >> 16); hi = max(hi & 0xffffu, hi >> 16);
+                            tail = own.w >> 16;
+                        } else {
+                            const unsigned int a = g == 0 ? own.x : own.z, b = g == 0 ? own.y : own.w;
+                            lo = __vminu4(a, b); hi = __vmaxu4(a, b);
+                            lo = __vminu4(lo, lo >> 16); hi = __vmaxu4(hi, hi >> 16);
+                            lo = min(lo & 0xffu, (lo >> 8) & 0xffu); hi = max(hi & 0xffu, (hi >> 8) & 0xffu);
+                            tail = b >> 24;
+                        }
+                        const int j_last = k * PER + g * 8 + 8;                       // padded index of the group's last voxel
+                        const int c0 = (j_last - 7) >> shift;
+                        atomicMin(&s_lo0[c0], lo); atomicMax(&s_hi0[c0], hi);
+                        if (extra) { atomicMin(&s_lo1[c0], lo); atomicMax(&s_hi1[c0], hi); }
+                        if ((j_last & (side - 1)) == 0) {                             // ... which also opens the next cell
+                            atomicMin(&s_lo0[c0 + 1], tail); atomicMax(&s_hi0[c0 + 1], tail);
+                            if (extra) { atomicMin(&s_lo1[c0 + 1], tail); atomicMax(&s_hi1[c0 + 1], tail); }
+                        }
+                    }
+                }
+            }
+        }
+        if (real_z) {
+            __syncthreads();
+            const int cy = jy0 >> shift, cz = jz >> shift;
+            const bool two_slabs = (jz & (side - 1)) == 0;                             // jz >= 1 here
+            for (int cx = threadIdx.x; cx < cnx; cx += 256) {
+                const unsigned int lo0 = s_lo0[cx], hi0 = s_hi0[cx];
+                if (lo0 <= hi0) {
+                    const size_t i = ((size_t)cz * cny + cy) * cnx + cx;
+                    atomicMin(gmin + i, lo0); atomicMax(gmax + i, hi0);
+                    if (two_slabs) { const size_t q = i - (size_t)cny * cnx; atomicMin(gmin + q, lo0); atomicMax(gmax + q, hi0); }
+                }
+                const unsigned int lo1 = s_lo1[cx], hi1 = s_hi1[cx];
+                if (two_bands && lo1 <= hi1) {
+                    const size_t i = ((size_t)cz * cny + (cy - 1)) * cnx + cx;
+                    atomicMin(gmin + i, lo1); atomicMax(gmax + i, hi1);
+                    if (two_slabs) { const size_t q = i - (size_t)cny * cnx; atomicMin(gmin + q, lo1); atomicMax(gmax + q, hi1); }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// 32-bit cell tables of pad_cells_kernel -> the product's 16-bit tables, plus the dataset min/max (= over all cells)
+__global__ void cell_table_finish_kernel(const unsigned int* __restrict__ gmin, const unsigned int* __restrict__ gmax, uint64_t ncells,
+                                         uint16_t* __restrict__ cmin, uint16_t* __restrict__ cmax, unsigned int* out_min, unsigned int* out_max)
+{
+    unsigned int lo = 0xffffffffu, hi = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned int a = gmin[i], b = gmax[i];
+        cmin[i] = (uint16_t)a; cmax[i] = (uint16_t)b;
+        lo = min(lo, a); hi = max(hi, b);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, lo); atomicMax(out_max, hi); }
+}
+
 // ---- z-pair words for the texpair kernel, derived from the padded volume -----------------------------
 // Layers [l0, l0+nl) of the z-pair array into a tightly packed staging buffer: word (x, y, L) =
 // v(x, y, max(L-1,0)) | v(x, y, min(L,nz-1)) << bits = padded(x+1, y+1, L) | padded(x+1, y+1, L+1) << bits.
@@ -312,7 +444,8 @@ __global__ void popcount_kernel(const unsigned int* __restrict__ bits, uint64_t 
 
 // ---- launch order of the march kernels' CTA tiles: longest rays first ---------------------------------------------
 // One CTA.  Pass 1: every tile's cost = the longest chord of its centre and corner rays through the box (computeRay /
-// intersectRayAABB, VolumeRenderer.cs:194-238, evaluated approximately -- it only orders work), quantised into 1024
+// intersectRayAABB, VolumeRenderer.cs:194-238, evaluated approximately -- it only orders work; centre + two opposite
+// corners), quantised into 1024
 // classes (class 0 = longest), histogram in shared memory.  Pass 2: exclusive scan of the classes.  Pass 3: scatter,
 // order[offset[class]++] = tile x | y << 16.  Every tile appears exactly once whatever the atomics' order.
 __device__ __forceinline__ float ray_chord(const FrameConsts& fc, float pxc, float pyc)
@@ -353,16 +486,28 @@ cta_order_kernel(const __grid_constant__ FrameConsts fc, int row0, int row_end, 
         const int l0 = row0 + by * px_h, l1 = min(l0 + px_h, row_end) - 1;
         const float y0 = (float)min(owned_row_to_global(fc, l0), fc.H - 1) + 0.5f, y1 = (float)min(owned_row_to_global(fc, l1), fc.H - 1) + 0.5f;
         const float x0 = (float)(bx * px_w) + 0.5f, x1 = (float)min(bx * px_w + px_w, fc.W) - 0.5f;
-        const float c = fmaxf(fmaxf(fmaxf(ray_chord(fc, x0, y0), ray_chord(fc, x1, y0)), fmaxf(ray_chord(fc, x0, y1), ray_chord(fc, x1, y1))),
-                              ray_chord(fc, 0.5f * (x0 + x1), 0.5f * (y0 + y1)));
+        const float c = fmaxf(fmaxf(ray_chord(fc, x0, y0), ray_chord(fc, x1, y1)), ray_chord(fc, 0.5f * (x0 + x1), 0.5f * (y0 + y1)));
         const int cls = CLASSES - 1 - min(max((int)(c * scale), 0), CLASSES - 1);
         scratch[i] = (uint32_t)cls;
         atomicAdd(&s_count[cls], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                                              // exclusive scan, 1024 classes
-        unsigned int run = 0u;
-        for (int k = 0; k < CLASSES; ++k) { const unsigned int v = s_count[k]; s_count[k] = run; run += v; }
+    {                                                                    // exclusive scan, 1024 classes = one per thread
+        __shared__ unsigned int s_warp[32];
+        const unsigned int v = s_count[threadIdx.x];
+        unsigned int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d); if ((threadIdx.x & 31) >= d) inc += u; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = s_warp[threadIdx.x], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, winc, d); if (threadIdx.x >= d) winc += u; }
+            s_warp[threadIdx.x] = winc - w;
+        }
+        __syncthreads();
+        s_count[threadIdx.x] = s_warp[threadIdx.x >> 5] + inc - v;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -569,7 +569,7 @@ int lab_launch_texpair(const LaunchPlan& plan, const vr::MarchArgs& a, int W, in
 // runs on the draining machine at the end of the grid are the short rays.  Lab r2 (B200, headline frame): 2.47 -> 2.36 ms
 // on the full frame, 1.10 -> 0.94 ms at the oblique camera K1, 0.443 -> 0.355 ms on a 1/8 partition.  Only the ORDER in
 // which the hardware starts the tiles changes; every pixel is computed by the same code from the same inputs.  The table
-// is built on the GPU by one small kernel in the frame's stream (cta_order_kernel: chord of each tile's centre and corner
+// is built on the GPU by one small kernel in the frame's stream (cta_order_kernel: chord of each tile's centre and two corner
 // rays through the box, counting sort over 1024 length classes) and only when its key -- camera, box, partition, band --
 // changes; one table per band.  VR_LPT=0 turns it off.
 const uint32_t* cta_order_for(vr_context* c, const LaunchPlan& plan, dim3 grid, int px_w, int px_h, int row0, int row_end, cudaStream_t s)
@@ -694,9 +694,9 @@ void release_volume(vr_context* c)
 }
 
 // Volume ingest from a device-resident x-fastest source (RendererCore.cpp:360-419 on the GPU):
-//   pass 1  pad_minmax_kernel   ONE read of the source: edge-replicated linear copy + min/max
+//   pass 1  pad_cells_kernel    ONE read of the source: edge-replicated linear copy + per-cell min/max table + min/max
+//                               (source rows 16-byte aligned; otherwise pad_minmax_kernel, and cell_minmax_kernel as pass 3)
 //   pass 2  histogram_kernel    (needs the max of pass 1 for the 16-bit binning, RendererCore.cpp:386-398)
-//   pass 3  cell_minmax_kernel  per-cell min/max table (reads the padded copy ~1.1x)
 // The layered arrays are built later, from the padded copy, by the first frame that needs them.  Everything is
 // allocated into locals first; the context is only touched once nothing can fail any more.
 // Peak footprint during the call: source + padded copy (+ the previous volume until the swap).
@@ -705,22 +705,55 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
 {
     const int nx = (int)dims[0], ny = (int)dims[1], nz = (int)dims[2];
     const uint64_t n = (uint64_t)nx * ny * nz;
-    DevBuf mm, bins, hlut, padded, cmin, cmax, cempty;
+    DevBuf mm, bins, hlut, padded, cmin, cmax, cempty, cell32;
     VR_CUDA(mm.alloc(2 * sizeof(unsigned int)));
     VR_CUDA(bins.alloc(256 * sizeof(unsigned long long)));
     const unsigned int init[2] = {0xffffffffu, 0u};
     VR_CUDA(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     VR_CUDA(cudaMemsetAsync(bins.p, 0, 256 * sizeof(unsigned long long), c->stream));
 
-    // pass 1: padded copy + min/max
+    // cell table geometry: smallest cell side >= 8 voxels with at most 65536 cells (the empty map then stays resident
+    // in L1 / shared memory next to the texture working set)
+    int shift = 3;
+    auto cells_of = [&](int sh, int a) { return (int)(dims[a] >> sh) + 1; };
+    while ((uint64_t)cells_of(shift, 0) * cells_of(shift, 1) * cells_of(shift, 2) > 65536ull) ++shift;
+    const int cnx = cells_of(shift, 0), cny = cells_of(shift, 1), cnz = cells_of(shift, 2);
+    const uint64_t ncells = (uint64_t)cnx * cny * cnz;
+    VR_CUDA(cmin.alloc(ncells * sizeof(uint16_t)));
+    VR_CUDA(cmax.alloc(ncells * sizeof(uint16_t)));
+    VR_CUDA(cempty.alloc(((ncells + 31) / 32) * sizeof(uint32_t)));
+
+    // pass 1: padded copy + min/max (+ the cell table when the source rows are 16-byte aligned: ONE read of the source)
     const uint32_t pitch = (uint32_t)(round_up((uint64_t)(nx + 2) * sizeof(T), 16) / sizeof(T));
     const uint64_t slice = (uint64_t)pitch * (uint64_t)(ny + 2);
     const uint64_t bytes = slice * (uint64_t)(nz + 2) * sizeof(T) + 256;
     VR_CUDA(padded.alloc(bytes));
     VR_CUDA(cudaMemsetAsync(static_cast<char*>(padded.p) + bytes - 256, 0, 256, c->stream));
-    vr::pad_minmax_kernel<T><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, padded.as<T>(), nx, ny, nz, pitch,
-                                                                      mm.as<unsigned int>(), mm.as<unsigned int>() + 1);
-    VR_CUDA(cudaGetLastError());
+    static const bool no_fused = [] { const char* e = std::getenv("VR_INGEST_FUSED"); return e && std::atoi(e) == 0; }();
+    const bool fused = !no_fused && nx % (16 / (int)sizeof(T)) == 0 && (reinterpret_cast<uintptr_t>(d_src) & 15) == 0;
+    if (fused) {
+        VR_CUDA(cell32.alloc(2 * ncells * sizeof(unsigned int)));
+        unsigned int* gmin = cell32.as<unsigned int>(), *gmax = gmin + ncells;
+        VR_CUDA(cudaMemsetAsync(gmin, 0xff, ncells * sizeof(unsigned int), c->stream));
+        VR_CUDA(cudaMemsetAsync(gmax, 0, ncells * sizeof(unsigned int), c->stream));
+        const uint64_t passes = (uint64_t)((ny + 2 + 7) / 8) * (uint64_t)(nz + 2);
+        // grid = exactly what is resident at once: the kernel is grid-stride over equal passes, a partial second round of
+        // CTAs would leave most of the machine idle at the end
+        const size_t cells_smem = 4 * (size_t)cnx * sizeof(unsigned int);
+        int per_sm = 0;
+        VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vr::pad_cells_kernel<T>, 256, cells_smem));
+        if (per_sm < 1) per_sm = 1;
+        vr::pad_cells_kernel<T><<<(unsigned)std::min<uint64_t>(passes, (uint64_t)c->sm_count * per_sm), 256, cells_smem, c->stream>>>(
+            d_src, padded.as<T>(), nx, ny, nz, pitch, shift, cnx, cny, gmin, gmax);
+        VR_CUDA(cudaGetLastError());
+        vr::cell_table_finish_kernel<<<(unsigned)std::min<uint64_t>((ncells + 255) / 256, 64), 256, 0, c->stream>>>(
+            gmin, gmax, ncells, cmin.as<uint16_t>(), cmax.as<uint16_t>(), mm.as<unsigned int>(), mm.as<unsigned int>() + 1);
+        VR_CUDA(cudaGetLastError());
+    } else {
+        vr::pad_minmax_kernel<T><<<c->sm_count * 16, 256, 0, c->stream>>>(d_src, padded.as<T>(), nx, ny, nz, pitch,
+                                                                          mm.as<unsigned int>(), mm.as<unsigned int>() + 1);
+        VR_CUDA(cudaGetLastError());
+    }
     unsigned int mmh[2] = {0, 255};
     VR_CUDA(cudaMemcpyAsync(mmh, mm.p, sizeof mmh, cudaMemcpyDeviceToHost, c->stream));
     VR_CUDA(cudaStreamSynchronize(c->stream));
@@ -740,19 +773,12 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
     unsigned long long hbins[256];
     VR_CUDA(cudaMemcpyAsync(hbins, bins.p, sizeof hbins, cudaMemcpyDeviceToHost, c->stream));
 
-    // pass 3: cell table.  Smallest cell side >= 8 voxels with at most 65536 cells: the empty map then stays
-    // resident in L1 next to the texture working set.
-    int shift = 3;
-    auto cells_of = [&](int sh, int a) { return (int)(dims[a] >> sh) + 1; };
-    while ((uint64_t)cells_of(shift, 0) * cells_of(shift, 1) * cells_of(shift, 2) > 65536ull) ++shift;
-    const int cnx = cells_of(shift, 0), cny = cells_of(shift, 1), cnz = cells_of(shift, 2);
-    const uint64_t ncells = (uint64_t)cnx * cny * cnz;
-    VR_CUDA(cmin.alloc(ncells * sizeof(uint16_t)));
-    VR_CUDA(cmax.alloc(ncells * sizeof(uint16_t)));
-    VR_CUDA(cempty.alloc(((ncells + 31) / 32) * sizeof(uint32_t)));
-    vr::cell_minmax_kernel<T><<<(unsigned)std::min<uint64_t>(ncells, (uint64_t)c->sm_count * 32), 128, 0, c->stream>>>(
-        padded.as<T>(), pitch, slice, nx, ny, nz, shift, cnx, cny, cnz, cmin.as<uint16_t>(), cmax.as<uint16_t>());
-    VR_CUDA(cudaGetLastError());
+    // pass 3 (only when pass 1 could not build it): cell table from the padded copy
+    if (!fused) {
+        vr::cell_minmax_kernel<T><<<(unsigned)std::min<uint64_t>(ncells, (uint64_t)c->sm_count * 32), 128, 0, c->stream>>>(
+            padded.as<T>(), pitch, slice, nx, ny, nz, shift, cnx, cny, cnz, cmin.as<uint16_t>(), cmax.as<uint16_t>());
+        VR_CUDA(cudaGetLastError());
+    }
     VR_CUDA(cudaStreamSynchronize(c->stream));          // also completes the D2H copy into `hbins`
 
     // nothing can fail from here: swap the new volume in
