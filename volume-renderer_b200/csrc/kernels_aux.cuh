@@ -251,8 +251,9 @@ __global__ void cell_empty_kernel(const uint16_t* __restrict__ cmax, uint64_t nc
 // 8-bit: bin = value; 16-bit: bin = round(value * 255.0f / max_dataset_val) as the reference computes
 // it (float multiply, IEEE divide, round half away, assignment to uint16_t :394); bin 0 and bins > 255
 // are skipped.  The 16-bit mapping depends on the value only, so it is tabulated once per upload
-// (65536 entries, 0 = skip) and the scan itself is an HBM-bound read: 16-byte loads, the table in
-// shared memory, one 256-bin counter set per warp, runs of equal bins merged before the atomic.
+// (65536 entries, 0 = skip; only entries [0, dataset max] are ever read, so only those are staged: 4 KB instead of
+// 64 KB for 12-bit data, which triples the resident CTAs) and the scan itself is an HBM-bound read: 16-byte loads, the
+// table in shared memory, one 256-bin counter set per warp, runs of equal bins merged before the atomic.
 __global__ void histogram_lut_kernel(float max_dataset_val, uint8_t* __restrict__ lut)
 {
     const unsigned int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,16 +267,16 @@ constexpr int HIST_THREADS = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(HIST_THREADS)
-histogram_kernel(const T* __restrict__ src, uint64_t n, const uint8_t* __restrict__ lut, unsigned long long* out_bins)
+histogram_kernel(const T* __restrict__ src, uint64_t n, const uint8_t* __restrict__ lut, int lut_entries, unsigned long long* out_bins)
 {
     extern __shared__ __align__(16) unsigned char hist_smem[];
     unsigned int* wbins = reinterpret_cast<unsigned int*>(hist_smem);                  // [warps][256]
-    uint8_t* slut = hist_smem + (HIST_THREADS / 32) * 256 * sizeof(unsigned int);        // [65536], 16-bit data only
+    uint8_t* slut = hist_smem + (HIST_THREADS / 32) * 256 * sizeof(unsigned int);        // [lut_entries], 16-bit data only
     for (int i = threadIdx.x; i < (HIST_THREADS / 32) * 256; i += blockDim.x) wbins[i] = 0;
     if (sizeof(T) == 2) {
         const uint4* g = reinterpret_cast<const uint4*>(lut);
         uint4* d = reinterpret_cast<uint4*>(slut);
-        for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) d[i] = __ldg(g + i);
+        for (int i = threadIdx.x; i < lut_entries / 16; i += blockDim.x) d[i] = __ldg(g + i);   // entries [0, dataset max], rounded up to 16
     }
     __syncthreads();
     unsigned int* mine = wbins + (threadIdx.x >> 5) * 256;

@@ -505,66 +505,6 @@ void launch_nearest_s(const LaunchPlan& plan, const vr::MarchArgs& a, dim3 grid,
     }
 }
 
-#ifdef VR_LAB
-// development builds only (tools/lab/build_lab.sh): pipeline depth / occupancy variants of the DVR form, chosen per
-// launch through the environment: VR_LAB_TP="depth,minb"; returns -1 when the frame / variant is not covered
-template <typename T, int DEPTH, int MINW, bool SKIP, int CTAW, int WX = (CTAW < 4 ? CTAW : 4)>
-int lab_tp(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s)
-{
-    using namespace vr;
-    typedef CtaShape<CTAW, WX> S;
-    const dim3 grid((W + S::PX - 1) / S::PX, (row_end - row0 + S::PY - 1) / S::PY);
-    MarchArgs b = a; b.grid_ctas = grid.x * grid.y;
-    if (CTAW != VR_CTA_WARPS || WX != VR_CTA_WX) b.cta_order = nullptr;   // the table is built for the product's tile shape
-#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINW, CTAW, WX><<<grid, S::THREADS, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, b)
-    if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
-    if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
-    if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
-#undef VR_K
-    return -1;
-}
-template <typename T, bool SKIP>
-int lab_tp_s(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int depth, int minb, int ctaw)
-{
-    // minb = resident warps per SM (register budget), ctaw = warps per CTA
-    const int key = depth * 10000 + minb * 100 + ctaw;
-    switch (key) {
-        case 24808: return lab_tp<T, 2, 48, SKIP, 8>(plan, a, W, row0, row_end, s);
-        case 33208: return lab_tp<T, 3, 32, SKIP, 8>(plan, a, W, row0, row_end, s);
-        case 34008: return lab_tp<T, 3, 40, SKIP, 8>(plan, a, W, row0, row_end, s);
-        case 43208: return lab_tp<T, 4, 32, SKIP, 8>(plan, a, W, row0, row_end, s);
-        case 43204: return lab_tp<T, 4, 32, SKIP, 4>(plan, a, W, row0, row_end, s);
-        case 43202: return lab_tp<T, 4, 32, SKIP, 2>(plan, a, W, row0, row_end, s);
-        case 43201: return lab_tp<T, 4, 32, SKIP, 1>(plan, a, W, row0, row_end, s);
-        case 33604: return lab_tp<T, 3, 36, SKIP, 4>(plan, a, W, row0, row_end, s);
-        case 33602: return lab_tp<T, 3, 36, SKIP, 2>(plan, a, W, row0, row_end, s);
-        case 43604: return lab_tp<T, 4, 36, SKIP, 4>(plan, a, W, row0, row_end, s);
-        case 43602: return lab_tp<T, 4, 36, SKIP, 2>(plan, a, W, row0, row_end, s);
-        case 34004: return lab_tp<T, 3, 40, SKIP, 4>(plan, a, W, row0, row_end, s);
-        case 34002: return lab_tp<T, 3, 40, SKIP, 2>(plan, a, W, row0, row_end, s);
-        // squarer tiles: ctaw code 42 = 4 warps as 16x8 px, 21 = 2 warps as 8x8, 82 = 8 warps as 16x16, 41 = 4 warps as 8x16
-        case 43242: return lab_tp<T, 4, 32, SKIP, 4, 2>(plan, a, W, row0, row_end, s);
-        case 43221: return lab_tp<T, 4, 32, SKIP, 2, 1>(plan, a, W, row0, row_end, s);
-        case 43282: return lab_tp<T, 4, 32, SKIP, 8, 2>(plan, a, W, row0, row_end, s);
-        case 43241: return lab_tp<T, 4, 32, SKIP, 4, 1>(plan, a, W, row0, row_end, s);
-        case 33642: return lab_tp<T, 3, 36, SKIP, 4, 2>(plan, a, W, row0, row_end, s);
-        case 42442: return lab_tp<T, 4, 24, SKIP, 4, 2>(plan, a, W, row0, row_end, s);   // 70 registers: 7 CTAs of 4 warps, 52.8 instr/sample
-        case 32442: return lab_tp<T, 3, 24, SKIP, 4, 2>(plan, a, W, row0, row_end, s);
-        default: return -1;
-    }
-}
-int lab_launch_texpair(const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int bpv)
-{
-    const char* e = std::getenv("VR_LAB_TP");
-    int depth = 0, minb = 0, ctaw = 8;
-    if (!e || std::sscanf(e, "%d,%d,%d", &depth, &minb, &ctaw) < 2 || plan.form != vr::FORM_DVR) return -1;
-    if (bpv == 2) return plan.skip ? lab_tp_s<uint16_t, true>(plan, a, W, row0, row_end, s, depth, minb, ctaw)
-                                   : lab_tp_s<uint16_t, false>(plan, a, W, row0, row_end, s, depth, minb, ctaw);
-    return plan.skip ? lab_tp_s<uint8_t, true>(plan, a, W, row0, row_end, s, depth, minb, ctaw)
-                     : lab_tp_s<uint8_t, false>(plan, a, W, row0, row_end, s, depth, minb, ctaw);
-}
-#endif
-
 // Launch order of the CTA tiles: tiles sorted by the estimated length of their rays, longest first (LPT), so that what
 // runs on the draining machine at the end of the grid are the short rays.  Lab r2 (B200, headline frame): 2.47 -> 2.36 ms
 // on the full frame, 1.10 -> 0.94 ms at the oblique camera K1, 0.443 -> 0.355 ms on a 1/8 partition.  Only the ORDER in
@@ -609,6 +549,67 @@ const uint32_t* cta_order_for(vr_context* c, const LaunchPlan& plan, dim3 grid, 
     return t->d;
 }
 
+#ifdef VR_LAB
+// development builds only (tools/lab/build_lab.sh): pipeline depth / occupancy variants of the DVR form, chosen per
+// launch through the environment: VR_LAB_TP="depth,minb"; returns -1 when the frame / variant is not covered
+template <typename T, int DEPTH, int MINW, bool SKIP, int CTAW, int WX = (CTAW < 4 ? CTAW : 4)>
+int lab_tp(vr_context* c, const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s)
+{
+    using namespace vr;
+    typedef CtaShape<CTAW, WX> S;
+    const dim3 grid((W + S::PX - 1) / S::PX, (row_end - row0 + S::PY - 1) / S::PY);
+    MarchArgs b = a; b.grid_ctas = grid.x * grid.y;
+    b.cta_order = cta_order_for(c, plan, grid, S::PX, S::PY, row0, row_end, s);   // a table for this tile shape
+#define VR_K(TCDIV, WIN, UNIT, NOCAP) march_texpair_kernel<T, TCDIV, WIN, UNIT, NOCAP, FORM_DVR, DEPTH, SKIP, MINW, CTAW, WX><<<grid, S::THREADS, SKIP ? (size_t)a.cell_words * 4 : 0, s>>>(plan.fc, b)
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_COVERS0) { VR_K(DIV_RECIP_EXACT, WIN_COVERS0, true, true); return 0; }
+    if (plan.shape == SHAPE_UNIT && plan.win == WIN_CLAMP)   { VR_K(DIV_RECIP_EXACT, WIN_CLAMP, true, true); return 0; }
+    if (plan.shape == SHAPE_MARK && plan.win == WIN_CLAMP)   { VR_K(DIV_MARKSTEIN, WIN_CLAMP, false, true); return 0; }
+#undef VR_K
+    return -1;
+}
+template <typename T, bool SKIP>
+int lab_tp_s(vr_context* c, const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int depth, int minb, int ctaw)
+{
+    // minb = resident warps per SM (register budget), ctaw = warps per CTA
+    const int key = depth * 10000 + minb * 100 + ctaw;
+    switch (key) {
+        case 24808: return lab_tp<T, 2, 48, SKIP, 8>(c, plan, a, W, row0, row_end, s);
+        case 33208: return lab_tp<T, 3, 32, SKIP, 8>(c, plan, a, W, row0, row_end, s);
+        case 34008: return lab_tp<T, 3, 40, SKIP, 8>(c, plan, a, W, row0, row_end, s);
+        case 43208: return lab_tp<T, 4, 32, SKIP, 8>(c, plan, a, W, row0, row_end, s);
+        case 43204: return lab_tp<T, 4, 32, SKIP, 4>(c, plan, a, W, row0, row_end, s);
+        case 43202: return lab_tp<T, 4, 32, SKIP, 2>(c, plan, a, W, row0, row_end, s);
+        case 43201: return lab_tp<T, 4, 32, SKIP, 1>(c, plan, a, W, row0, row_end, s);
+        case 33604: return lab_tp<T, 3, 36, SKIP, 4>(c, plan, a, W, row0, row_end, s);
+        case 33602: return lab_tp<T, 3, 36, SKIP, 2>(c, plan, a, W, row0, row_end, s);
+        case 43604: return lab_tp<T, 4, 36, SKIP, 4>(c, plan, a, W, row0, row_end, s);
+        case 43602: return lab_tp<T, 4, 36, SKIP, 2>(c, plan, a, W, row0, row_end, s);
+        case 34004: return lab_tp<T, 3, 40, SKIP, 4>(c, plan, a, W, row0, row_end, s);
+        case 34002: return lab_tp<T, 3, 40, SKIP, 2>(c, plan, a, W, row0, row_end, s);
+        // squarer tiles: ctaw code 42 = 4 warps as 16x8 px, 21 = 2 warps as 8x8, 82 = 8 warps as 16x16, 41 = 4 warps as 8x16
+        case 43242: return lab_tp<T, 4, 32, SKIP, 4, 2>(c, plan, a, W, row0, row_end, s);
+        case 43221: return lab_tp<T, 4, 32, SKIP, 2, 1>(c, plan, a, W, row0, row_end, s);
+        case 43282: return lab_tp<T, 4, 32, SKIP, 8, 2>(c, plan, a, W, row0, row_end, s);
+        case 43241: return lab_tp<T, 4, 32, SKIP, 4, 1>(c, plan, a, W, row0, row_end, s);
+        case 33642: return lab_tp<T, 3, 36, SKIP, 4, 2>(c, plan, a, W, row0, row_end, s);
+        case 42442: return lab_tp<T, 4, 24, SKIP, 4, 2>(c, plan, a, W, row0, row_end, s);
+        case 42882: return lab_tp<T, 4, 28, SKIP, 4, 2>(c, plan, a, W, row0, row_end, s);   // 70 registers: 7 CTAs of 4 warps, 52.8 instr/sample
+        case 32442: return lab_tp<T, 3, 24, SKIP, 4, 2>(c, plan, a, W, row0, row_end, s);
+        default: return -1;
+    }
+}
+int lab_launch_texpair(vr_context* c, const LaunchPlan& plan, const vr::MarchArgs& a, int W, int row0, int row_end, cudaStream_t s, int bpv)
+{
+    const char* e = std::getenv("VR_LAB_TP");
+    int depth = 0, minb = 0, ctaw = 8;
+    if (!e || std::sscanf(e, "%d,%d,%d", &depth, &minb, &ctaw) < 2 || plan.form != vr::FORM_DVR) return -1;
+    if (bpv == 2) return plan.skip ? lab_tp_s<uint16_t, true>(c, plan, a, W, row0, row_end, s, depth, minb, ctaw)
+                                   : lab_tp_s<uint16_t, false>(c, plan, a, W, row0, row_end, s, depth, minb, ctaw);
+    return plan.skip ? lab_tp_s<uint8_t, true>(c, plan, a, W, row0, row_end, s, depth, minb, ctaw)
+                     : lab_tp_s<uint8_t, false>(c, plan, a, W, row0, row_end, s, depth, minb, ctaw);
+}
+#endif
+
 // the march.  `row0`/`row_end` select a band of this rank's local rows (compact row space); `peer_arrive` != null
 // fuses the hand-off signal into the kernel epilogue (returns *signalled = false when the kernel that ran cannot)
 int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int row_end, cudaStream_t s,
@@ -643,7 +644,7 @@ int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int ro
     if (plan.kernel == VR_KERNEL_TEXPAIR_PIPE) {
         a.tex = c->tex2;
 #ifdef VR_LAB
-        if (lab_launch_texpair(plan, a, c->W, row0, row_end, s, c->bpv) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
+        if (lab_launch_texpair(c, plan, a, c->W, row0, row_end, s, c->bpv) == 0) { VR_CUDA(cudaGetLastError()); return VR_OK; }
 #endif
         if (c->bpv == 2) { if (plan.skip) launch_texpair_ts<uint16_t, true>(plan, a, grid, s); else launch_texpair_ts<uint16_t, false>(plan, a, grid, s); }
         else             { if (plan.skip) launch_texpair_ts<uint8_t, true>(plan, a, grid, s);  else launch_texpair_ts<uint8_t, false>(plan, a, grid, s); }
@@ -761,13 +762,18 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
     // pass 2: histogram
     {
         size_t smem = (vr::HIST_THREADS / 32) * 256 * sizeof(unsigned int);
+        int lut_entries = 0;
         if (sizeof(T) == 2) {
             VR_CUDA(hlut.alloc(65536));
             vr::histogram_lut_kernel<<<65536 / 256, 256, 0, c->stream>>>((float)(int)mmh[1], hlut.as<uint8_t>());
-            smem += 65536;
+            lut_entries = (int)std::min<unsigned int>(65536u, (mmh[1] + 16u) & ~15u);      // values never exceed the dataset max
+            smem += (size_t)lut_entries;
             VR_CUDA(cudaFuncSetAttribute(vr::histogram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        vr::histogram_kernel<T><<<c->sm_count * 3, vr::HIST_THREADS, smem, c->stream>>>(d_src, n, hlut.as<uint8_t>(), bins.as<unsigned long long>());
+        int per_sm = 0;
+        VR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vr::histogram_kernel<T>, vr::HIST_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        vr::histogram_kernel<T><<<c->sm_count * per_sm, vr::HIST_THREADS, smem, c->stream>>>(d_src, n, hlut.as<uint8_t>(), lut_entries, bins.as<unsigned long long>());
         VR_CUDA(cudaGetLastError());
     }
     unsigned long long hbins[256];
