@@ -12,6 +12,7 @@ with vb.Context(64, 64) as ctx:
     ctx.upload_synthetic((1024, 1024, 1024), 2, 4095, workloads.SEEDS['C4'])
     ctx.set_camera(workloads.camera_block('K2'))
     ctx.set_params(vb.default_params(alpha_scale=0.02, min_val=1000, max_val=3000, filter=1)); ctx.render()
+    ctx.set_camera(workloads.camera_block('K1')); ctx.render()
     ctx.set_params(vb.default_params(alpha_scale=0.02, min_val=1000, max_val=3000, filter=0)); ctx.render()
 " > $O/launches_ingest.log 2>&1; echo "ingest launch list rc=$?"
 cap() {  # name kernel-regex workload-key bench-args...
@@ -31,5 +32,11 @@ cap texpair_C4_window_skip march_texpair_kernel "C4/K2/trilinear/0.05/1000-3000/
 cap texpair_C3_skip    march_texpair_kernel "C3/K2/trilinear/0.05/1000-3000/skip" --config C3 --alpha 0.05
 cap texpair_C2         march_texpair_kernel "C2/K2/trilinear/0.02/0-255" --config C2
 cap texpair_C5         march_texpair_kernel "C5/K2/trilinear/0.02/0-4095" --config C5
+# the fused ingest kernel (HBM-bound: padded copy + cell table + min/max in one read of the source) and the histogram
+for k in pad_cells histogram_kernel; do
+  timeout 600 $NCU -k regex:$k -c 1 -f -o $O/ncu_ingest_$k python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-count --no-dense > $O/ncu_ingest_$k.log 2>&1; echo "ncu ingest $k rc=$?"
+  python profiles/summarize_ncu.py $O/ncu_ingest_$k.ncu-rep $O/ncu_ingest_${k}_summary.txt > /dev/null 2>&1; head -n 3 $O/ncu_ingest_${k}_summary.txt
+  rm -f $O/ncu_ingest_$k.ncu-rep
+done
 ls -la $O | head -40
 cuobjdump -sass -fun $(cuobjdump -elf volume-renderer_b200/lib/libvolren_b200.so | grep -o "_ZN2vr20march_texpair_kernelItLi0ELi1ELb1ELb1ELi0ELi4ELb0ELi32ELi4ELi2EEEvNS_11FrameConstsENS_9MarchArgsE" | head -1) volume-renderer_b200/lib/libvolren_b200.so > $O/sass_texpair_headline.txt 2>&1
