@@ -386,27 +386,53 @@ def run_ours(args):
             if shared is not None:
                 shared.close()
             shared = None
-    e2e_mode = "single GPU: vr_render (row bands overlap the device->host copy)" if world == 1 else \
-               ("every rank copies its own row tiles (banded, overlapping its march) into a shared page-locked host frame, two frames in flight" if shared is not None
+    e2e_mode = ("single GPU: vr_render_submit / vr_render_wait, two frames in flight into two pinned host frames (row bands overlap each band's device->host copy); "
+                "e2e.sync_value = the synchronous vr_render, one frame at a time") if world == 1 else \
+               ("every rank copies its own row tiles (banded, overlapping its march) into a shared page-locked host frame; vr_render_submit / vr_render_wait, two frames in flight" if shared is not None
                 else "hand-off to rank 0 on the device, rank 0 copies the frame to the host")
+    pipelined = world == 1 or shared is not None
+    pinned2 = [pinned, torch.empty((H, W, 4), dtype=torch.float32).pin_memory()] if world == 1 else None
+    tickets = {}
+
+    def complete(g):
+        """frame g is in host memory (and, N > 1, every rank's rows of it: the consumer's hand-shake)"""
+        ctx.render_wait(tickets.pop(g))
+        if shared is not None:
+            shared.mark_done(g)
+            if rank == 0:
+                shared.wait_all_done(g)                               # the whole frame is in host memory
+                shared.release(g)
+
+    # synchronous figure beside the pipelined one (single GPU): vr_render, one frame at a time
+    sync_ms = None
+    if world == 1:
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                ts = time.perf_counter()
+            ctx.set_camera(cam)
+            ctx.set_params(params)
+            ctx.render_to_host_ptr(pinned.data_ptr())
+        sync_ms = (time.perf_counter() - ts) * 1e3 / args.steps
     barrier()
     t0 = time.perf_counter()
     for i in range(args.warmup + args.steps):
+        f = i + 1
         if i == args.warmup:                  # the end-to-end path warms up like the device path (first-call
+            if pipelined and (f - 1) in tickets:
+                complete(f - 1)               # nothing in flight when the clock starts
             barrier()                         # stream/event creation, first copies into the pinned frame)
             t0 = time.perf_counter()
         ctx.set_camera(cam)
         ctx.set_params(params)
-        if world == 1:
-            ctx.render_to_host_ptr(pinned.data_ptr())
-        elif shared is not None:
-            # two host frames: a rank may start frame i+1 while the consumer still waits for the slowest rank of frame i
-            shared.wait_writable(i + 1)                               # the buffer's previous frame (i - 1) has been consumed
-            ctx.render_owned_to_host_ptr(shared.buffer_ptr(i + 1))
-            shared.mark_done(i + 1)
-            if rank == 0:
-                shared.wait_all_done(i + 1)                           # the whole frame is in host memory
-                shared.release(i + 1)
+        if pipelined:
+            # two host frames: frame f is submitted while frame f - 1 is still on the GPU / on its way to the host
+            if shared is not None:
+                shared.wait_writable(f)                               # the buffer's previous frame (f - 2) has been consumed
+                tickets[f] = ctx.render_submit(shared.buffer_ptr(f))
+            else:
+                tickets[f] = ctx.render_submit(pinned2[f % 2].data_ptr())
+            if (f - 1) in tickets:
+                complete(f - 1)
         else:
             step(release=False)
             if rank == 0:
@@ -417,6 +443,8 @@ def run_ours(args):
                 else:
                     pinned.copy_(frame, non_blocking=True)
                     torch.cuda.synchronize()
+    if pipelined:
+        complete(args.warmup + args.steps)    # the last frame is in host memory before the clock stops
     barrier()
     e2e_s = time.perf_counter() - t0
     # a short timed region (multi-GPU frames take < 1 ms) can end before nvidia-smi has sampled it
@@ -438,6 +466,10 @@ def run_ours(args):
     # N-GPU frame == 1-GPU frame (every kernel is bit-exact and pixels are independent)
     same_as_single = None
     host_same = None
+    if world == 1:
+        # both host frames of the pipelined end-to-end loop hold the frame the device-timed loop left on the GPU
+        dev_frame = frame.cpu().numpy().view(np.uint32)
+        host_same = bool(all(np.array_equal(pb.numpy().view(np.uint32), dev_frame) for pb in pinned2))
     if world > 1:
         step(release=False)
         if rank == 0:
@@ -545,13 +577,14 @@ def run_ours(args):
         "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, hand-off: "
                                   + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory and their last CTA publishes the arrival in the frame barrier words of the same peer memory (no collective call, no signal kernel)", "nccl": "one NCCL gather + de-interleave"}[handoff],
                    "multi_gpu_frame_equals_single_gpu_frame": same_as_single,
-                   "e2e_path": e2e_mode, "multi_gpu_host_frame_equals_single_gpu_frame": host_same,
+                   "e2e_path": e2e_mode, "multi_gpu_host_frame_equals_single_gpu_frame": host_same if world > 1 else None, "host_frames_equal_device_frame": host_same,
                    "l2": f"inputs larger than L2 ({nvox * bpv / 2**30:.2f} GiB volume vs 126 MB L2); no flush needed" if nvox * bpv > 2**28
                          else "volume fits in L2 (correctness/plumbing config)",
                    "kernel": roof["kernel"]},
         "roofline": roof, "dense": dense, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "sync_value": (rays_per_frame / (sync_ms * 1e-3) / 1e6) if sync_ms else None, "sync_ms_per_step": sync_ms},
         "gpu_launches": timed_launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

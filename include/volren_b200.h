@@ -185,6 +185,16 @@ VR_API int vr_render_device(vr_context* ctx, float* d_rgba, int compact, void* c
  * (shared memory, page-locked in each) every GPU's own PCIe link carries its share of the frame.  Rows
  * owned by other ranks are left untouched.  Synchronous. */
 VR_API int vr_render_owned_to_host(vr_context* ctx, float* host_full_frame, vr_render_stats* stats);
+/* pipelined form of the two calls above (no reference counterpart: RendererCore::render blocks every frame on its
+ * timer query, RendererCore.cpp:152): vr_render_submit enqueues the frame -- this context's row tiles into their rows
+ * of the W x H host frame, exactly what vr_render_owned_to_host writes; the whole frame when world == 1 -- and returns a
+ * ticket at once; vr_render_wait blocks until that frame is complete in host memory and reports its stats (kernel_ms
+ * = first band's start to last band's end, which overlaps the neighbouring frames' work).  At most TWO frames may be
+ * in flight; the host buffers of frames in flight must differ and stay page-locked.  Setters that rewrite device state
+ * (a new transfer function, window minimum, partition, volume) wait for the frames in flight by themselves; the
+ * synchronous render calls refuse to run while a ticket is outstanding. */
+VR_API int vr_render_submit(vr_context* ctx, float* host_frame, uint32_t* ticket);
+VR_API int vr_render_wait(vr_context* ctx, uint32_t ticket, vr_render_stats* stats);
 /* rank-major compact tiles [world][owned rows][W][4] -> full frame, on the device
  * (the de-interleave after the NCCL gather) */
 VR_API int vr_assemble_tiles(vr_context* ctx, const float* d_gathered, float* d_frame,

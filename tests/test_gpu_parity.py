@@ -422,6 +422,54 @@ def test_launch_order_table_follows_camera_partition_and_bands():
                 assert np.array_equal(dev[owned].view(np.uint32), ref[owned].view(np.uint32)), f"device frame {i} rank {rank}/{world}"
 
 
+@pytest.mark.parametrize("W,H", [(1280, 724), (200, 150)])      # banded frames / one launch + tile copies
+def test_pipelined_host_frames_equal_synchronous_ones(W, H):
+    """vr_render_submit / vr_render_wait: two frames in flight into two host buffers, cameras changing every frame,
+    a window change and a partition change in mid-flight (both wait for the frames in flight by themselves): every
+    frame equals the one the synchronous call produces.  A third submit and a synchronous render are refused while
+    tickets are outstanding."""
+    vox, dims, bpv, vs = scenarios.volume("mix_64x64x32_u16")
+    cams = [scenarios.camera(k) for k in ("K0", "K1", "K2", "K1", "K0", "K2", "K1")]
+    kws = [dict(alpha_scale=0.05, min_val=0, max_val=4095, filter=1)] * 3 + [dict(alpha_scale=0.07, min_val=900, max_val=3000, filter=1)] * 2 + \
+          [dict(alpha_scale=0.07, min_val=900, max_val=3000, filter=0)] * 2
+    parts = [(0, 1)] * 5 + [(1, 2)] * 2
+    with vb.Context(W, H) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        refs = []
+        for cam, kw, (rank, world) in zip(cams, kws, parts):
+            ctx.set_partition(rank, world, 8)
+            ctx.set_camera(cam)
+            ctx.set_params(vb.default_params(**kw))
+            host = np.full((H, W, 4), np.float32(-1.0))
+            ctx.render_owned_to_host_ptr(host.ctypes.data)
+            refs.append(host)
+        bufs = [np.empty((H, W, 4), np.float32), np.empty((H, W, 4), np.float32)]
+        tickets = []
+        for i, (cam, kw, (rank, world)) in enumerate(zip(cams, kws, parts)):
+            ctx.set_partition(rank, world, 8)
+            ctx.set_camera(cam)
+            ctx.set_params(vb.default_params(**kw))
+            if i >= 2:                                    # the buffer is about to be reused: its frame must be complete
+                t, j = tickets.pop(0)
+                st = ctx.render_wait(t)
+                assert st.kernel_launches >= 1 and st.kernel_used == expected_kernel(kws[j])
+                assert np.array_equal(bufs[j % 2].view(np.uint32), refs[j].view(np.uint32)), f"frame {j}"
+            bufs[i % 2][:] = -1.0
+            tickets.append((ctx.render_submit(bufs[i % 2].ctypes.data), i))
+            if i == 1:
+                with pytest.raises(vb.VolrenError):       # two frames in flight already
+                    ctx.render_submit(bufs[0].ctypes.data)
+                with pytest.raises(vb.VolrenError):       # the synchronous calls refuse to run meanwhile
+                    ctx.render()
+        for t, j in tickets:
+            ctx.render_wait(t)
+            assert np.array_equal(bufs[j % 2].view(np.uint32), refs[j].view(np.uint32)), f"frame {j}"
+        with pytest.raises(vb.VolrenError):
+            ctx.render_wait(tickets[-1][0])               # already collected
+        img, _ = ctx.render()                             # and the synchronous path works again
+        assert img.shape == (H, W, 4)
+
+
 # ---------------------------------------------------------------- ingest
 
 def test_volume_stats_match_reference_loops():

@@ -144,6 +144,8 @@ struct vr_context {
     vr_params params;
     float* d_lut = nullptr;              // [0,256): the caller's LUT; [256,512): host-finalised opacity
     bool lut_fast_ok = false;            // every LUT entry finite and >= +0
+    float lut_final_host[256];           // what [256,512) of d_lut holds (uploaded only when it changes)
+    bool lut_final_valid = false;
     int rank = 0, world = 1, tile_rows = 8;
     // Markstein verification cache: divisor bits -> ok
     std::map<uint32_t, bool> div_ok;
@@ -162,6 +164,12 @@ struct vr_context {
     cudaStream_t band_stream[BANDS] = {};
     cudaEvent_t band_kdone[BANDS] = {}, band_cdone[BANDS] = {};
     bool bands_ready = false;
+    // frames in flight of the pipelined host path (vr_render_submit / vr_render_wait)
+    struct FrameSlot { cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr; uint32_t launches = 0; int kernel = 0; bool skip = false, pending = false; };
+    static constexpr int SLOTS = 2;
+    FrameSlot slot[SLOTS];
+    uint32_t next_ticket = 1;            // ticket t lives in slot t % SLOTS
+    uint32_t slot_ticket[SLOTS] = {0, 0};
 };
 
 namespace {
@@ -284,10 +292,19 @@ bool ensure_zpair_array(vr_context* c)
 }
 
 // empty map for the window's lower bound: cell empty <=> cell max <= min_val
+// Frames of the pipelined host path that are still in flight read the context's device state (LUTs, empty-cell map,
+// launch-order tables, layered arrays): anything that rewrites such state waits for them first.  The tickets stay valid.
+int drain_in_flight(vr_context* c)
+{
+    for (auto& f : c->slot) if (f.pending) VR_CUDA(cudaEventSynchronize(f.done));
+    return VR_OK;
+}
+
 int ensure_empty_map(vr_context* c, int32_t min_val)
 {
     if (!c->d_cell_max) return fail(VR_ERR_NO_VOLUME, "no cell table");
     if (c->empty_valid && c->empty_thresh == min_val) return VR_OK;
+    { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }
     VR_CUDA(cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned long long), c->stream));
     vr::cell_empty_kernel<<<std::max<int>(1, (int)std::min<uint64_t>((c->ncells + 255) / 256, (uint64_t)c->sm_count * 8)), 256, 0, c->stream>>>(
         c->d_cell_max, c->ncells, (unsigned int)min_val, c->d_cell_bits, c->d_cell_count);
@@ -361,9 +378,11 @@ int make_plan(vr_context* c, int compact, LaunchPlan* plan)
             fin[i] = (float)(1.0 - std::pow(1.0 - (double)a, (double)p.step_scale));
             fast = std::isfinite(fin[i]) && fin[i] >= 0.0f && !std::signbit(fin[i]);
         }
-        if (fast) {
+        if (fast && !(c->lut_final_valid && std::memcmp(c->lut_final_host, fin, sizeof fin) == 0)) {
+            { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }
             VR_CUDA(cudaMemcpyAsync(c->d_lut + 256, fin, sizeof fin, cudaMemcpyHostToDevice, c->stream));
             VR_CUDA(cudaStreamSynchronize(c->stream));      // `fin` is on the stack
+            std::memcpy(c->lut_final_host, fin, sizeof fin); c->lut_final_valid = true;
         }
     }
     if (!fast) tcdiv = vr::DIV_IEEE;
@@ -706,6 +725,7 @@ int ingest_from_device(vr_context* c, const T* d_src, const uint64_t dims[3])
 {
     const int nx = (int)dims[0], ny = (int)dims[1], nz = (int)dims[2];
     const uint64_t n = (uint64_t)nx * ny * nz;
+    { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }
     DevBuf mm, bins, hlut, padded, cmin, cmax, cempty, cell32;
     VR_CUDA(mm.alloc(2 * sizeof(unsigned int)));
     VR_CUDA(bins.alloc(256 * sizeof(unsigned long long)));
@@ -907,6 +927,12 @@ void vr_destroy(vr_context* c)
         if (c->band_kdone[b]) cudaEventDestroy(c->band_kdone[b]);
         if (c->band_cdone[b]) cudaEventDestroy(c->band_cdone[b]);
     }
+    for (auto& f : c->slot) {
+        if (f.pending) cudaEventSynchronize(f.done);
+        if (f.ev0) cudaEventDestroy(f.ev0);
+        if (f.ev1) cudaEventDestroy(f.ev1);
+        if (f.done) cudaEventDestroy(f.done);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1042,7 +1068,9 @@ int vr_set_params(vr_context* c, const vr_params* p)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown kernel (AUTO, DIRECT, TEXPAIR_PIPE, NEAREST_TEX)");
     if (p->empty_skip < VR_SKIP_AUTO || p->empty_skip > VR_SKIP_OFF)
         return fail(VR_ERR_INVALID, "vr_set_params: unknown empty_skip mode");
+    if (std::memcmp(p, &c->params, sizeof *p) == 0) return VR_OK;          // unchanged (a per-frame caller): nothing to do
     if (p->use_tf) {
+        { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }
         // the optimised loop tests ranges on float bit patterns: it needs a finite, non-negative opacity LUT
         bool ok = true;
         for (int i = 0; i < 256; ++i) ok = ok && std::isfinite(p->tf_lut[i]) && p->tf_lut[i] >= 0.0f && !std::signbit(p->tf_lut[i]);
@@ -1067,6 +1095,7 @@ int vr_set_partition(vr_context* c, int rank, int world, int tile_rows)
     if (!c) return fail(VR_ERR_INVALID, "vr_set_partition: null context");
     if (world < 1 || rank < 0 || rank >= world || tile_rows < 1)
         return fail(VR_ERR_INVALID, "vr_set_partition: need 0 <= rank < world and tile_rows >= 1");
+    if (rank != c->rank || world != c->world || tile_rows != c->tile_rows) { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }
     c->rank = rank; c->world = world; c->tile_rows = tile_rows;
     return VR_OK;
 }
@@ -1119,7 +1148,20 @@ static int ensure_bands(vr_context* c)
 // cost 0.7 ms per 1080p frame when copied after the whole march).  `full_frame` = 1: unpartitioned frame, the
 // host buffer receives every row (vr_render); 0: the rank's row tiles land in their rows of a full host frame
 // that other ranks fill too (vr_render_owned_to_host).  The device image is compact (owned rows only).
-static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats)
+static int ensure_slot(vr_context::FrameSlot& f)
+{
+    if (f.done) return VR_OK;
+    VR_CUDA(cudaEventCreate(&f.ev0));
+    VR_CUDA(cudaEventCreate(&f.ev1));
+    VR_CUDA(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    return VR_OK;
+}
+
+// Enqueues the frame -- march of every band, each followed in its own stream by the device->host copy of its rows --
+// and returns without waiting.  `f.done` fires when the whole frame is in host memory, `f.ev0 -> f.ev1` brackets the
+// marches.  Band b of the NEXT frame is ordered, by its stream, after band b's copy of this one: two frames can be in
+// flight on the one device image, and the host's work for a frame overlaps the GPU's work on the one before.
+static int render_banded_submit(vr_context* c, float* host_rgba, vr_context::FrameSlot& f)
 {
     const int B = band_count((size_t)c->W * (size_t)compact_rows_of(c->H, c->rank, c->world, c->tile_rows));
     int rc = ensure_bands(c);
@@ -1133,13 +1175,12 @@ static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats
     const size_t row_floats = (size_t)c->W * 4;
     uint32_t launches = 0;
     int nb = 0;
-    cudaError_t e = cudaEventRecord(c->ev0, c->stream);
+    cudaError_t e = cudaEventRecord(f.ev0, c->band_stream[0]);             // band 0 is the first to start
     for (int b = 0; b < B && rc == VR_OK && e == cudaSuccess; ++b) {
         const int t0 = b * tiles_per_band, t1 = std::min(local_tiles, t0 + tiles_per_band);
         if (t0 >= t1) break;
         cudaStream_t bs = c->band_stream[b];
-        e = cudaStreamWaitEvent(bs, c->ev0, 0);
-        if (e == cudaSuccess) rc = launch_march(c, plan, c->d_frame, t0 * T, t1 * T, bs, nullptr, nullptr);
+        rc = launch_march(c, plan, c->d_frame, t0 * T, t1 * T, bs, nullptr, nullptr);
         ++launches;
         if (e == cudaSuccess) e = cudaEventRecord(c->band_kdone[b], bs);
         // The band's tiles are T*W*16-byte chunks, contiguous in the compact device image and world*T rows apart in
@@ -1162,18 +1203,39 @@ static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats
         if (e == cudaSuccess) e = cudaEventRecord(c->band_cdone[b], bs);
         nb = b + 1;
     }
+    // join on the context's stream: it only ever carries these waits and records, so frames do not serialise on it
     for (int b = 0; b < nb && e == cudaSuccess; ++b) e = cudaStreamWaitEvent(c->stream, c->band_kdone[b], 0);
-    if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);           // every band's march has finished
+    if (e == cudaSuccess) e = cudaEventRecord(f.ev1, c->stream);            // every band's march has finished
     for (int b = 0; b < nb && e == cudaSuccess; ++b) e = cudaStreamWaitEvent(c->stream, c->band_cdone[b], 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(f.done, c->stream);           // the frame is in host memory
     if (e != cudaSuccess || rc != VR_OK) {
         for (int b = 0; b < nb; ++b) cudaStreamSynchronize(c->band_stream[b]);
+        cudaStreamSynchronize(c->stream);
         return e != cudaSuccess ? cuda_fail(e, "banded render") : rc;
     }
-    float ms = 0.f;
-    VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    fill_stats(stats, ms, launches, plan);
+    f.launches = launches; f.kernel = plan.kernel; f.skip = plan.skip;
     return VR_OK;
+}
+
+static int frame_slot_wait(vr_context* c, vr_context::FrameSlot& f, vr_render_stats* stats)
+{
+    (void)c;
+    VR_CUDA(cudaEventSynchronize(f.done));
+    float ms = 0.f;
+    VR_CUDA(cudaEventElapsedTime(&ms, f.ev0, f.ev1));
+    if (stats) { stats->kernel_ms = ms; stats->kernel_launches = f.launches; stats->kernel_used = (uint32_t)f.kernel; stats->skip_used = f.skip ? 1u : 0u; }
+    return VR_OK;
+}
+
+static int render_banded(vr_context* c, float* host_rgba, vr_render_stats* stats)
+{
+    // synchronous form: no frame may be in flight (the caller of vr_render_submit waits for its tickets first)
+    vr_context::FrameSlot& f = c->slot[0];
+    int rc = ensure_slot(f);
+    if (rc != VR_OK) return rc;
+    rc = render_banded_submit(c, host_rgba, f);
+    if (rc != VR_OK) return rc;
+    return frame_slot_wait(c, f, stats);
 }
 
 static bool banding_pays(const vr_context* c)
@@ -1187,6 +1249,7 @@ static bool banding_pays(const vr_context* c)
 int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
 {
     if (!c || !host_rgba) return fail(VR_ERR_INVALID, "vr_render: null argument");
+    if (c->slot[0].pending || c->slot[1].pending) return fail(VR_ERR_INVALID, "vr_render: frames submitted with vr_render_submit are still in flight");
     VR_CUDA(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     const size_t bytes = (size_t)c->W * c->H * 4 * sizeof(float);
@@ -1213,6 +1276,7 @@ int vr_render(vr_context* c, float* host_rgba, vr_render_stats* stats)
 int vr_render_owned_to_host(vr_context* c, float* host_full_frame, vr_render_stats* stats)
 {
     if (!c || !host_full_frame) return fail(VR_ERR_INVALID, "vr_render_owned_to_host: null argument");
+    if (c->slot[0].pending || c->slot[1].pending) return fail(VR_ERR_INVALID, "vr_render_owned_to_host: frames submitted with vr_render_submit are still in flight");
     VR_CUDA(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     int rc;
@@ -1235,6 +1299,59 @@ int vr_render_owned_to_host(vr_context* c, float* host_full_frame, vr_render_sta
     }
     if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return VR_OK;
+}
+
+// Pipelined form of vr_render / vr_render_owned_to_host: vr_render_submit enqueues the frame and returns a ticket,
+// vr_render_wait blocks until that frame is complete in host memory.  Up to two frames may be in flight; the host's
+// per-frame work (planning, launches, the consumer's hand-shake) then overlaps the GPU's work on the previous frame.
+int vr_render_submit(vr_context* c, float* host_frame, uint32_t* ticket)
+{
+    if (!c || !host_frame || !ticket) return fail(VR_ERR_INVALID, "vr_render_submit: null argument");
+    VR_CUDA(cudaSetDevice(c->device));
+    const uint32_t t = c->next_ticket;
+    vr_context::FrameSlot& f = c->slot[t % vr_context::SLOTS];
+    if (f.pending) return fail(VR_ERR_INVALID, "vr_render_submit: two frames are already in flight; wait for the older ticket first");
+    int rc = ensure_slot(f);
+    if (rc != VR_OK) return rc;
+    if (banding_pays(c)) {
+        rc = render_banded_submit(c, host_frame, f);
+        if (rc != VR_OK) return rc;
+    } else {
+        // small frames: one launch and the copies of the owned tiles, all in the context's stream
+        LaunchPlan plan;
+        rc = make_plan(c, /*compact=*/1, &plan);
+        if (rc != VR_OK) return rc;
+        VR_CUDA(cudaEventRecord(f.ev0, c->stream));
+        rc = launch_march(c, plan, c->d_frame, 0, plan.local_rows, c->stream, nullptr, nullptr);
+        if (rc != VR_OK) return rc;
+        VR_CUDA(cudaEventRecord(f.ev1, c->stream));
+        const int tiles = (c->H + c->tile_rows - 1) / c->tile_rows;
+        const size_t row_floats = (size_t)c->W * 4;
+        int local_tile = 0;
+        for (int tl = c->rank; tl < tiles; tl += c->world, ++local_tile) {
+            const int y0 = tl * c->tile_rows, rows = std::min(c->tile_rows, c->H - y0);
+            VR_CUDA(cudaMemcpyAsync(host_frame + (size_t)y0 * row_floats, c->d_frame + (size_t)local_tile * c->tile_rows * row_floats,
+                                    (size_t)rows * row_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+        VR_CUDA(cudaEventRecord(f.done, c->stream));
+        f.launches = plan.local_rows > 0 ? 1u : 0u; f.kernel = plan.kernel; f.skip = plan.skip;
+    }
+    f.pending = true;
+    c->slot_ticket[t % vr_context::SLOTS] = t;
+    c->next_ticket = t + 1;
+    *ticket = t;
+    return VR_OK;
+}
+
+int vr_render_wait(vr_context* c, uint32_t ticket, vr_render_stats* stats)
+{
+    if (!c) return fail(VR_ERR_INVALID, "vr_render_wait: null context");
+    vr_context::FrameSlot& f = c->slot[ticket % vr_context::SLOTS];
+    if (!f.pending || c->slot_ticket[ticket % vr_context::SLOTS] != ticket) return fail(VR_ERR_INVALID, "vr_render_wait: no such frame in flight");
+    VR_CUDA(cudaSetDevice(c->device));
+    const int rc = frame_slot_wait(c, f, stats);
+    f.pending = false;
+    return rc;
 }
 
 int vr_read_frame(vr_context* c, float* host_rgba)

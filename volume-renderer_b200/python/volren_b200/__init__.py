@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "vr_upload_volume", "vr_upload_volume_device", "vr_set_voxel_size", "vr_volume_stats_get",
     "vr_cell_table_get", "vr_memory_info_get", "vr_render_peer", "vr_peer_frame_reset",
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
-    "vr_render", "vr_read_frame", "vr_render_device", "vr_render_owned_to_host", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
+    "vr_render", "vr_read_frame", "vr_render_device", "vr_render_owned_to_host", "vr_render_submit", "vr_render_wait", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
     "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
     "vr_peer_frame_arrive", "vr_peer_frame_release", "vr_peer_frame_status",
     "vr_upload_synthetic", "vr_synthetic_to_host",
@@ -116,6 +116,8 @@ def lib():
         L.vr_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_read_frame.argtypes = [C.c_void_p, C.c_void_p]
         L.vr_render_owned_to_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
+        L.vr_render_submit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.vr_render_wait.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RenderStats)]
         L.vr_render_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(RenderStats)]
         L.vr_assemble_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vr_read_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -271,6 +273,19 @@ class Context:
         """This rank's row tiles into their rows of a full host frame (shared by all ranks)."""
         st = RenderStats()
         _check(lib().vr_render_owned_to_host(self._h, C.c_void_p(host_full_frame_ptr), C.byref(st)))
+        return st
+
+    def render_submit(self, host_frame_ptr: int) -> int:
+        """Pipelined form of render_owned_to_host_ptr (the whole frame when world == 1): enqueue and return a ticket;
+        at most two frames in flight, each into its own page-locked host buffer."""
+        t = C.c_uint32(0)
+        _check(lib().vr_render_submit(self._h, C.c_void_p(host_frame_ptr), C.byref(t)))
+        return t.value
+
+    def render_wait(self, ticket: int):
+        """Block until the frame of `ticket` is complete in host memory."""
+        st = RenderStats()
+        _check(lib().vr_render_wait(self._h, C.c_uint32(ticket), C.byref(st)))
         return st
 
     def render_device(self, dptr: int, compact: bool = False, stream: int = 0):
