@@ -290,13 +290,21 @@ def run_ours(args):
     launches = [0]
     used = [0, 0]
 
-    # fused hand-off: every rank maps rank 0's frame (NVLink peer memory) and renders into it
-    peer_ptr = 0
+    # fused hand-off: every rank maps rank 0's TWO target frames (NVLink peer memory) and renders into them alternately
+    peer_ptrs = []
+    ctx_b = None                              # rank 0: a second context that only owns the second target frame
+    cstream = None                            # rank 0: consumer stream (arrival wait + release), so its marches are not held back
+    mstreams = None                           # one march stream per target frame: the tail of frame f overlaps the head of frame f + 1
     handoff = args.handoff if world > 1 else "none"
     if handoff == "peer":
         ok = 1
         try:
-            peer_ptr = vdist.open_peer_frame(ctx, dst=0)
+            if rank == 0:
+                ctx_b = vb.Context(W, H, device=local_rank)
+                cstream = torch.cuda.Stream()
+            peer_ptrs.append(vdist.open_peer_frame(ctx, dst=0))
+            peer_ptrs.append(vdist.open_peer_frame(ctx_b if rank == 0 else ctx, dst=0))
+            mstreams = [torch.cuda.Stream(), torch.cuda.Stream()]
         except Exception as e:              # e.g. CUDA IPC unavailable in this container
             ok = 0
             if rank == 0:
@@ -307,22 +315,40 @@ def run_ours(args):
             handoff = "nccl"
 
     frame_no = [0]
+    peer_uses = [0, 0]                        # frames rendered into each target frame so far
+
+    def peer_target(f):
+        """target frame of frame f: (buffer index, device pointer, its use count including f)"""
+        b = f % 2
+        return b, peer_ptrs[b], (f + 1) // 2 if b == 1 else f // 2
+
+    if handoff == "peer":                     # which kernel / form runs (the asynchronous calls below do not report it)
+        st0 = ctx.render_device(local.data_ptr(), compact=True, stream=sptr)
+        used[0], used[1] = st0.kernel_used, st0.skip_used
 
     def step(release=True):
         if world == 1:
             st = ctx.render_device(frame.data_ptr(), compact=False, stream=sptr)
         elif handoff == "peer":
-            # no collective call at all: completion and reuse of rank 0's frame are ordered by the
-            # barrier words behind its pixels (NVLink peer memory); the arrival is published by the march kernel itself
+            # no collective call and no host synchronisation at all: completion and reuse of rank 0's frames are ordered
+            # by the barrier words behind their pixels (NVLink peer memory).  Every rank: wait (on the device) until the
+            # target frame's previous occupant has been consumed, march -- the kernel's last CTA publishes the arrival.
+            # Rank 0, on its consumer stream: wait for all arrivals, consume, release.  Two target frames let every rank
+            # run one frame ahead of the consumer, so the marches of consecutive frames run back to back.
             frame_no[0] += 1
-            if rank != 0:
-                ctx.peer_frame_release(peer_ptr, frame_no[0] - 1, is_owner=False, stream=sptr)
+            b, ptr, u = peer_target(frame_no[0])
+            peer_uses[b] = u
+            mptr = mstreams[b].cuda_stream
+            ctx.peer_frame_release(ptr, u - 1, is_owner=False, stream=mptr)
+            ctx.render_peer(ptr, frame_no[0], world, is_owner=False, stream=mptr, wait=False)
+            launches[0] += 2
+            if rank == 0:
+                ctx.peer_frame_wait_arrivals(ptr, u, world, stream=cstream.cuda_stream)
                 launches[0] += 1
-            # the march kernel's last CTA publishes this rank's arrival (no signal kernel); rank 0 then waits for all
-            st = ctx.render_peer(peer_ptr, frame_no[0], world, is_owner=(rank == 0), stream=sptr)
-            if rank == 0 and release:
-                ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)
-                launches[0] += 1
+                if release:
+                    ctx.peer_frame_release(ptr, u, is_owner=True, stream=cstream.cuda_stream)
+                    launches[0] += 1
+            return
         else:
             st = ctx.render_device(local.data_ptr(), compact=True, stream=sptr)
             vdist.gather_tiles(local, gathered, dst=0)
@@ -356,12 +382,23 @@ def run_ours(args):
     idle_samples = len(sampler.rows)        # taken before the GPU was under load: not reported
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    if mstreams is not None and handoff == "peer":
+        for m in mstreams:
+            m.wait_event(ev0)                 # the march streams start after the clock
+    first_timed = frame_no[0] + 1
     for _ in range(args.steps):
         step()
+    if mstreams is not None and handoff == "peer":
+        for m in mstreams:
+            stream.wait_stream(m)             # every march has finished ...
+    if cstream is not None:
+        stream.wait_stream(cstream)           # ... and rank 0 has seen all arrivals of the last frame before the clock stops
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     timed_launches = launches[0]
+    if handoff == "peer":                     # the marches' CUDA-event brackets of the timed frames (ring of 64 in the library)
+        kernel_ms.extend(ctx.peer_kernel_ms(f) for f in range(max(first_timed, frame_no[0] - 63), frame_no[0] + 1))
     timed_kernel_ms = list(kernel_ms)
 
     # e2e: through the C-ABI with host buffers, copies inside the timed region.
@@ -437,9 +474,10 @@ def run_ours(args):
             step(release=False)
             if rank == 0:
                 if handoff == "peer":
-                    torch.cuda.current_stream().synchronize()       # arrival wait done: the frame is complete
-                    ctx.read_frame_into(pinned.data_ptr())
-                    ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)   # consumed: may be overwritten
+                    b, ptr, u = peer_target(frame_no[0])
+                    cstream.synchronize()                           # arrival wait done: the frame is complete
+                    (ctx if b == 0 else ctx_b).read_frame_into(pinned.data_ptr())
+                    ctx.peer_frame_release(ptr, u, is_owner=True, stream=cstream.cuda_stream)   # consumed: may be overwritten
                 else:
                     pinned.copy_(frame, non_blocking=True)
                     torch.cuda.synchronize()
@@ -474,9 +512,12 @@ def run_ours(args):
         step(release=False)
         if rank == 0:
             torch.cuda.synchronize()
-            multi = torch.from_numpy(ctx.read_frame()).to(dev) if handoff == "peer" else frame.clone()
             if handoff == "peer":
-                ctx.peer_frame_release(peer_ptr, frame_no[0], is_owner=True, stream=sptr)
+                b, ptr, u = peer_target(frame_no[0])
+                multi = torch.from_numpy((ctx if b == 0 else ctx_b).read_frame()).to(dev)
+                ctx.peer_frame_release(ptr, u, is_owner=True, stream=cstream.cuda_stream)
+            else:
+                multi = frame.clone()
         barrier()
         if rank == 0:
             ctx.set_partition(0, 1, TILE_ROWS)
@@ -492,9 +533,11 @@ def run_ours(args):
         barrier()
 
     if handoff == "peer" and rank == 0:
-        pst = ctx.peer_frame_status(peer_ptr)
-        if pst["timed_out"] or pst["arrivals"] != frame_no[0] * world:
-            raise SystemExit(f"bench.py: peer-memory frame barrier failed: {pst}, expected {frame_no[0] * world} arrivals")
+        torch.cuda.synchronize()
+        for b in (0, 1):
+            pst = ctx.peer_frame_status(peer_ptrs[b])
+            if pst["timed_out"] or pst["arrivals"] != peer_uses[b] * world:
+                raise SystemExit(f"bench.py: peer-memory frame barrier failed on target frame {b}: {pst}, expected {peer_uses[b] * world} arrivals")
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -505,8 +548,9 @@ def run_ours(args):
         if world > 1:
             torch.distributed.barrier()
         shared.close()
-    if peer_ptr and rank != 0:
-        ctx.frame_close_ipc(peer_ptr)
+    if peer_ptrs and rank != 0:
+        for ptr in peer_ptrs:
+            ctx.frame_close_ipc(ptr)
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -575,7 +619,7 @@ def run_ours(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "parallelism": f"screen-row tiles of {TILE_ROWS} rows interleaved over {world} GPU(s), replicated volume, hand-off: "
-                                  + {"none": "n/a", "peer": "march kernels store into rank 0's frame over NVLink peer memory and their last CTA publishes the arrival in the frame barrier words of the same peer memory (no collective call, no signal kernel)", "nccl": "one NCCL gather + de-interleave"}[handoff],
+                                  + {"none": "n/a", "peer": "march kernels (one stream per target frame, so consecutive frames overlap) store into one of rank 0's two target frames over NVLink peer memory and their last CTA publishes the arrival in the frame barrier words of the same peer memory; rank 0 waits / releases on a consumer stream (no collective call, no signal kernel, no host synchronisation between frames)", "nccl": "one NCCL gather + de-interleave"}[handoff],
                    "multi_gpu_frame_equals_single_gpu_frame": same_as_single,
                    "e2e_path": e2e_mode, "multi_gpu_host_frame_equals_single_gpu_frame": host_same if world > 1 else None, "host_frames_equal_device_frame": host_same,
                    "l2": f"inputs larger than L2 ({nvox * bpv / 2**30:.2f} GiB volume vs 126 MB L2); no flush needed" if nvox * bpv > 2**28
@@ -588,6 +632,8 @@ def run_ours(args):
         "gpu_launches": timed_launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+    if ctx_b is not None:
+        ctx_b.close()
     ctx.close()
     if world > 1:
         torch.distributed.destroy_process_group()

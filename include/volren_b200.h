@@ -231,6 +231,13 @@ VR_API int vr_peer_frame_status(vr_context* ctx, float* d_target_frame, uint32_t
  * vr_peer_frame_reset is called: a torn frame is never consumed silently. */
 VR_API int vr_render_peer(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int world, int is_owner,
                           void* cuda_stream, vr_render_stats* stats);
+/* stats == NULL makes vr_render_peer ASYNCHRONOUS (nothing is waited for; frames run back to back in the stream);
+ * vr_peer_kernel_ms then returns the march-kernel time of that call's frame_no (ring of the last 64 frames; it
+ * waits for that kernel).  vr_peer_frame_wait_arrivals enqueues only the owner's wait for frame_no * world arrivals,
+ * on a stream of the caller's choice -- on a consumer stream the owner's own march kernels are not held back by the
+ * slowest rank (with two target frames every rank then runs one frame ahead of the consumer). */
+VR_API int vr_peer_kernel_ms(vr_context* ctx, uint32_t frame_no, float* ms);
+VR_API int vr_peer_frame_wait_arrivals(vr_context* ctx, float* d_target_frame, uint32_t frame_no, int world, void* cuda_stream);
 VR_API int vr_peer_frame_reset(vr_context* ctx, float* d_target_frame);
 
 /* ---- display/save step after the path: float RGBA -> RGB8 (clamp, no gamma), vertical

@@ -138,6 +138,85 @@ def test_peer_memory_frame_barrier(tmp_path, world, fused):
     assert np.load(out)[0] == 1
 
 
+def _worker_two_target_frames(rank, world, port, out_path):
+    """bench.py's peer hand-off: TWO target frames on rank 0, asynchronous marches (vr_render_peer with stats == NULL),
+    the owner's arrival wait + release on a consumer stream.  No host synchronisation and no collective inside the
+    frame loop on the producing ranks; rank 0 checks every frame bit for bit."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python"), os.path.join(ROOT, "tests")]
+    os.environ["VR_PEER_TIMEOUT_MS"] = "60000"
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import volren_b200 as vb
+    import scenarios
+    dev = rank if torch.cuda.device_count() >= world else 0
+    torch.cuda.set_device(dev)
+    vox, dims, bpv, vs = scenarios.volume("mix64_u8")
+    cam = scenarios.camera("K1")
+    W, H, tile_rows = 200, 150, 8
+    alphas = [0.05, 0.4, 0.11, 0.9, 0.02, 0.3, 0.07]
+    ok = 1
+    with vb.Context(W, H, device=dev) as ctx:
+        ctx.upload_volume(vox, dims, vs)
+        ctx.set_camera(cam)
+        refs = []
+        if rank == 0:
+            for a in alphas:
+                ctx.set_params(vb.default_params(alpha_scale=a, min_val=0, max_val=255, filter=1))
+                refs.append(ctx.render()[0])
+        ctx_b = vb.Context(W, H, device=dev) if rank == 0 else None      # owns the second target frame, nothing else
+        handles = [[ctx.frame_export_ipc(), ctx_b.frame_export_ipc()] if rank == 0 else None]
+        dist.broadcast_object_list(handles, src=0)
+        ptrs = [ctx.frame_device_ptr(), ctx_b.frame_device_ptr()] if rank == 0 else [ctx.frame_open_ipc(h) for h in handles[0]]
+        cstream = torch.cuda.Stream() if rank == 0 else None
+        ctx.set_partition(rank, world, tile_rows)
+        dist.barrier()                                               # setup only
+        uses = [0, 0]
+        for f in range(1, len(alphas) + 1):
+            b = f % 2
+            uses[b] += 1
+            u = uses[b]
+            ctx.set_params(vb.default_params(alpha_scale=alphas[f - 1], min_val=0, max_val=255, filter=1))
+            ctx.peer_frame_release(ptrs[b], u - 1, is_owner=False)   # device-side wait: the frame's previous occupant was consumed
+            assert ctx.render_peer(ptrs[b], f, world, is_owner=False, wait=False) is None
+            if rank == 0:
+                ctx.peer_frame_wait_arrivals(ptrs[b], u, world, stream=cstream.cuda_stream)
+                cstream.synchronize()                                # consumer: the frame is complete
+                got = (ctx if b == 0 else ctx_b).read_frame()
+                if not np.array_equal(got.view(np.uint32), refs[f - 1].view(np.uint32)):
+                    ok = 0
+                    print(f"frame {f}: {int((got.view(np.uint32) != refs[f - 1].view(np.uint32)).any(axis=(1, 2)).sum())} rows differ", flush=True)
+                ctx.peer_frame_release(ptrs[b], u, is_owner=True, stream=cstream.cuda_stream)
+        ms = [ctx.peer_kernel_ms(f) for f in range(1, len(alphas) + 1)]
+        if not all(m > 0.0 for m in ms):
+            ok = 0
+            print(f"rank {rank}: kernel times {ms}", flush=True)
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            for b in (0, 1):
+                st = ctx.peer_frame_status(ptrs[b])
+                if st["timed_out"] or st["arrivals"] != uses[b] * world or st["released"] != uses[b]:
+                    ok = 0
+                    print(f"target frame {b}: status {st}, expected {uses[b] * world} arrivals, {uses[b]} released", flush=True)
+        okt = torch.tensor([ok])
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            np.save(out_path, np.array([int(okt.item())]))
+        dist.barrier()
+        if rank != 0:
+            for p in ptrs:
+                ctx.frame_close_ipc(p)
+        if ctx_b is not None:
+            ctx_b.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_target_frames_asynchronous_hand_off(tmp_path, world):
+    out = str(tmp_path / "ok.npy")
+    mp.spawn(_worker_two_target_frames, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert np.load(out)[0] == 1
+
+
 def test_a_barrier_timeout_is_reported_not_swallowed(monkeypatch):
     """a wait that gives up must surface.  One process plays the owner of a 2-rank frame whose peer never
     arrives: the bounded wait times out, the NEXT hand-off call fails with VR_ERR_TIMEOUT until the caller resets."""

@@ -151,9 +151,11 @@ struct vr_context {
     std::map<uint32_t, bool> div_ok;
     unsigned int* d_flag = nullptr;
     // fused peer hand-off
-    unsigned int* d_done = nullptr;      // CTAs finished (march kernel epilogue)
+    unsigned int* d_done = nullptr;      // CTAs finished (march kernel epilogue): 4 counters, frame_no & 3, so that consecutive
+                                         // frames marching concurrently on different streams do not share one
+    int done_slot = 0;
     // launch order of the CTA tiles (longest rays first), one table per band, rebuilt on the GPU when its key changes
-    struct OrderTable { uint32_t* d = nullptr; size_t cap = 0; cudaStream_t last = nullptr; std::vector<unsigned char> key; };
+    struct OrderTable { uint32_t* d = nullptr; size_t cap = 0; cudaEvent_t built = nullptr; std::vector<cudaStream_t> users; std::vector<unsigned char> key; };   // users: streams whose kernels may still read it
     static constexpr int ORDER_TABLES = 12;
     OrderTable order[ORDER_TABLES];
     int order_evict = 0;
@@ -164,6 +166,10 @@ struct vr_context {
     cudaStream_t band_stream[BANDS] = {};
     cudaEvent_t band_kdone[BANDS] = {}, band_cdone[BANDS] = {};
     bool bands_ready = false;
+    // march-kernel brackets of asynchronous vr_render_peer calls (stats == NULL), read back by vr_peer_kernel_ms
+    static constexpr int PEER_EVENTS = 64;
+    cudaEvent_t peer_ev[PEER_EVENTS][2] = {};
+    uint32_t peer_ev_frame[PEER_EVENTS] = {};
     // frames in flight of the pipelined host path (vr_render_submit / vr_render_wait)
     struct FrameSlot { cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr; uint32_t launches = 0; int kernel = 0; bool skip = false, pending = false; };
     static constexpr int SLOTS = 2;
@@ -550,11 +556,15 @@ const uint32_t* cta_order_for(vr_context* c, const LaunchPlan& plan, dim3 grid, 
     if (!t) for (auto& o : c->order) if (o.key.empty()) { t = &o; break; }
     if (!t) { t = &c->order[c->order_evict]; c->order_evict = (c->order_evict + 1) % vr_context::ORDER_TABLES; }
     if (t->key.size() == sizeof key && std::memcmp(t->key.data(), &key, sizeof key) == 0 && t->d) {
-        if (t->last != s) { if (t->last && cudaStreamSynchronize(t->last) != cudaSuccess) return nullptr; t->last = s; }
+        if (std::find(t->users.begin(), t->users.end(), s) == t->users.end()) {
+            // another stream than the one that built the table: order this stream's kernels behind the build
+            if (cudaStreamWaitEvent(s, t->built, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            t->users.push_back(s);
+        }
         return t->d;
     }
-    // rebuild.  A kernel of an earlier frame on ANOTHER stream may still read the table: wait for that stream first
-    if (t->last && t->last != s && cudaStreamSynchronize(t->last) != cudaSuccess) return nullptr;
+    // rebuild.  Kernels of earlier frames on OTHER streams may still read the table: wait for those streams first
+    for (cudaStream_t u : t->users) if (u != s && cudaStreamSynchronize(u) != cudaSuccess) return nullptr;
     if (2 * n > t->cap) {
         if (t->d) { cudaDeviceSynchronize(); cudaFree(t->d); }
         t->d = nullptr; t->cap = 0; t->key.clear();
@@ -563,8 +573,10 @@ const uint32_t* cta_order_for(vr_context* c, const LaunchPlan& plan, dim3 grid, 
     }
     vr::cta_order_kernel<<<1, 1024, 0, s>>>(fc, row0, row_end, px_w, px_h, (int)grid.x, (int)grid.y, t->d, t->d + n);
     if (cudaGetLastError() != cudaSuccess) { t->key.clear(); return nullptr; }
+    if (!t->built && cudaEventCreateWithFlags(&t->built, cudaEventDisableTiming) != cudaSuccess) { t->built = nullptr; t->key.clear(); cudaGetLastError(); return nullptr; }
+    if (cudaEventRecord(t->built, s) != cudaSuccess) { t->key.clear(); cudaGetLastError(); return nullptr; }
     t->key.assign(reinterpret_cast<unsigned char*>(&key), reinterpret_cast<unsigned char*>(&key) + sizeof key);
-    t->last = s;
+    t->users.assign(1, s);
     return t->d;
 }
 
@@ -657,7 +669,7 @@ int launch_march(vr_context* c, LaunchPlan& plan, float* d_out, int row0, int ro
     // 8: 1.69, 16: 1.72 -- what a checkpoint costs is not its ~25 instructions but the lanes that idle while others leap
     static const int check_every = [] { const char* e = std::getenv("VR_SKIP_CHECK"); const int v = e ? std::atoi(e) : 8; return (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : 8; }();
     a.skip_check_mask = check_every - 1;
-    a.done_counter = c->d_done; a.peer_arrive = peer_arrive; a.grid_ctas = grid.x * grid.y;
+    a.done_counter = c->d_done + (c->done_slot & 3); a.peer_arrive = peer_arrive; a.grid_ctas = grid.x * grid.y;
     a.cta_order = cta_order_for(c, plan, grid, Shape::PX, Shape::PY, row0, row_end, s);
     if (signalled) *signalled = peer_arrive != nullptr;
     if (plan.kernel == VR_KERNEL_TEXPAIR_PIPE) {
@@ -900,8 +912,8 @@ int vr_create(int device, int width, int height, vr_context** out)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_lut, 512 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_flag, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->d_lut, 0, 512 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_done, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_done, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaHostAlloc(&c->h_peer_error, sizeof(unsigned int), cudaHostAllocMapped);
     if (e == cudaSuccess) { *c->h_peer_error = 0; e = cudaHostGetDevicePointer(&c->d_peer_error, c->h_peer_error, 0); }
     if (e != cudaSuccess) { int rc = cuda_fail(e, "vr_create"); vr_destroy(c); return rc; }
@@ -916,7 +928,7 @@ void vr_destroy(vr_context* c)
     release_volume(c);
     if (c->d_cell_count) cudaFree(c->d_cell_count);
     if (c->d_done) cudaFree(c->d_done);
-    for (auto& o : c->order) if (o.d) cudaFree(o.d);
+    for (auto& o : c->order) { if (o.d) cudaFree(o.d); if (o.built) cudaEventDestroy(o.built); }
     if (c->h_peer_error) cudaFreeHost(c->h_peer_error);
     if (c->d_frame) cudaFree(c->d_frame);
     if (c->d_rgb8) cudaFree(c->d_rgb8);
@@ -927,6 +939,7 @@ void vr_destroy(vr_context* c)
         if (c->band_kdone[b]) cudaEventDestroy(c->band_kdone[b]);
         if (c->band_cdone[b]) cudaEventDestroy(c->band_cdone[b]);
     }
+    for (auto& pe : c->peer_ev) { if (pe[0]) cudaEventDestroy(pe[0]); if (pe[1]) cudaEventDestroy(pe[1]); }
     for (auto& f : c->slot) {
         if (f.pending) cudaEventSynchronize(f.done);
         if (f.ev0) cudaEventDestroy(f.ev0);
@@ -1489,19 +1502,55 @@ int vr_render_peer(vr_context* c, float* d_target_frame, uint32_t frame_no, int 
     rc = make_plan(c, /*compact=*/0, &plan);
     if (rc != VR_OK) return rc;
     bool signalled = false;
-    VR_CUDA(cudaEventRecord(c->ev0, s));
+    c->done_slot = (int)(frame_no & 3u);          // concurrent frames (different streams) must differ in frame_no mod 4
+    // stats == NULL: asynchronous -- nothing is waited for; the march's bracket goes into a ring of event pairs that
+    // vr_peer_kernel_ms reads later (frames then run back to back, the host never idles the GPU between them)
+    cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+    if (!stats) {
+        const int k = (int)(frame_no % vr_context::PEER_EVENTS);
+        if (!c->peer_ev[k][0]) { VR_CUDA(cudaEventCreate(&c->peer_ev[k][0])); VR_CUDA(cudaEventCreate(&c->peer_ev[k][1])); }
+        e0 = c->peer_ev[k][0]; e1 = c->peer_ev[k][1]; c->peer_ev_frame[k] = frame_no;
+    }
+    VR_CUDA(cudaEventRecord(e0, s));
     rc = launch_march(c, plan, d_target_frame, 0, plan.local_rows, s, &sync[0], &signalled);
     if (rc != VR_OK) return rc;
     uint32_t launches = plan.local_rows > 0 ? 1u : 0u;
     if (!signalled) { vr::peer_signal_kernel<<<1, 1, 0, s>>>(sync); ++launches; }
-    VR_CUDA(cudaEventRecord(c->ev1, s));
+    VR_CUDA(cudaEventRecord(e1, s));
     if (is_owner) { vr::peer_wait_kernel<<<1, 1, 0, s>>>(sync, 0, frame_no * (uint32_t)world, peer_timeout_ns(), c->d_peer_error); ++launches; }
     VR_CUDA(cudaGetLastError());
+    if (!stats) return VR_OK;
     VR_CUDA(cudaEventSynchronize(c->ev1));
     float ms = 0.f;
     VR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     fill_stats(stats, ms, launches, plan);
-    if (stats) stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return VR_OK;
+}
+
+// march-kernel time of an asynchronous vr_render_peer call (stats == NULL) for `frame_no`; waits for that kernel
+int vr_peer_kernel_ms(vr_context* c, uint32_t frame_no, float* ms)
+{
+    if (!c || !ms) return fail(VR_ERR_INVALID, "vr_peer_kernel_ms: null argument");
+    const int k = (int)(frame_no % vr_context::PEER_EVENTS);
+    if (!c->peer_ev[k][0] || c->peer_ev_frame[k] != frame_no) return fail(VR_ERR_INVALID, "vr_peer_kernel_ms: that frame's bracket is no longer kept (ring of 64)");
+    VR_CUDA(cudaSetDevice(c->device));
+    VR_CUDA(cudaEventSynchronize(c->peer_ev[k][1]));
+    VR_CUDA(cudaEventElapsedTime(ms, c->peer_ev[k][0], c->peer_ev[k][1]));
+    return VR_OK;
+}
+
+// the frame owner's side of the barrier on a stream of its own choice (e.g. a consumer stream, so that the owner's
+// march kernels are not held back by the slowest rank): wait until `frame_no * world` arrivals have been published
+int vr_peer_frame_wait_arrivals(vr_context* c, float* d_target_frame, uint32_t frame_no, int world, void* cuda_stream)
+{
+    if (!c || !d_target_frame || world < 1) return fail(VR_ERR_INVALID, "vr_peer_frame_wait_arrivals: bad argument");
+    int rc = peer_error_check(c, "vr_peer_frame_wait_arrivals");
+    if (rc != VR_OK) return rc;
+    VR_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream;
+    vr::peer_wait_kernel<<<1, 1, 0, s>>>(frame_sync_words(c, d_target_frame), 0, frame_no * (uint32_t)world, peer_timeout_ns(), c->d_peer_error);
+    VR_CUDA(cudaGetLastError());
     return VR_OK;
 }
 

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "vr_version", "vr_last_error", "vr_params_default", "vr_device_count",
     "vr_create", "vr_destroy", "vr_resize", "vr_image_size",
     "vr_upload_volume", "vr_upload_volume_device", "vr_set_voxel_size", "vr_volume_stats_get",
-    "vr_cell_table_get", "vr_memory_info_get", "vr_render_peer", "vr_peer_frame_reset",
+    "vr_cell_table_get", "vr_memory_info_get", "vr_render_peer", "vr_peer_frame_reset", "vr_peer_kernel_ms", "vr_peer_frame_wait_arrivals",
     "vr_set_camera", "vr_set_params", "vr_get_params", "vr_set_partition", "vr_owned_rows",
     "vr_render", "vr_read_frame", "vr_render_device", "vr_render_owned_to_host", "vr_render_submit", "vr_render_wait", "vr_assemble_tiles", "vr_read_rgb8", "vr_count_frame",
     "vr_frame_device_ptr", "vr_frame_export_ipc", "vr_frame_open_ipc", "vr_frame_close_ipc",
@@ -129,6 +129,8 @@ def lib():
         L.vr_peer_frame_release.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.vr_peer_frame_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.vr_render_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(RenderStats)]
+        L.vr_peer_kernel_ms.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+        L.vr_peer_frame_wait_arrivals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.vr_peer_frame_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.vr_cell_table_get.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int * 3), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.vr_memory_info_get.argtypes = [C.c_void_p, C.POINTER(MemoryInfo)]
@@ -332,12 +334,27 @@ class Context:
         _check(lib().vr_peer_frame_status(self._h, C.c_void_p(target_ptr), C.byref(a), C.byref(r), C.byref(t)))
         return {"arrivals": a.value, "released": r.value, "timed_out": t.value}
 
-    def render_peer(self, target_ptr: int, frame_no: int, world: int, is_owner: bool, stream: int = 0):
-        """Render this rank's tiles into the (own or peer) frame; the kernel's last CTA signals the arrival."""
+    def render_peer(self, target_ptr: int, frame_no: int, world: int, is_owner: bool, stream: int = 0, wait: bool = True):
+        """Render this rank's tiles into the (own or peer) frame; the kernel's last CTA signals the arrival.
+        wait=False: asynchronous (returns None; peer_kernel_ms(frame_no) reads the march time later)."""
+        if not wait:
+            _check(lib().vr_render_peer(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, world, 1 if is_owner else 0,
+                                        C.c_void_p(stream) if stream else None, None))
+            return None
         st = RenderStats()
         _check(lib().vr_render_peer(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, world, 1 if is_owner else 0,
                                     C.c_void_p(stream) if stream else None, C.byref(st)))
         return st
+
+    def peer_kernel_ms(self, frame_no: int) -> float:
+        ms = C.c_float(0.0)
+        _check(lib().vr_peer_kernel_ms(self._h, frame_no & 0xffffffff, C.byref(ms)))
+        return ms.value
+
+    def peer_frame_wait_arrivals(self, target_ptr: int, frame_no: int, world: int, stream: int = 0):
+        """Owner side, on a stream of its choice: wait until every rank has arrived for `frame_no`."""
+        _check(lib().vr_peer_frame_wait_arrivals(self._h, C.c_void_p(target_ptr), frame_no & 0xffffffff, world,
+                                                 C.c_void_p(stream) if stream else None))
 
     def peer_frame_reset(self, target_ptr: int = 0):
         _check(lib().vr_peer_frame_reset(self._h, C.c_void_p(target_ptr) if target_ptr else None))
