@@ -925,6 +925,7 @@ void vr_destroy(vr_context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();             // frames in flight, asynchronous peer frames
     release_volume(c);
     if (c->d_cell_count) cudaFree(c->d_cell_count);
     if (c->d_done) cudaFree(c->d_done);
@@ -958,6 +959,7 @@ int vr_resize(vr_context* c, int width, int height)
     if (width < 1 || height < 1 || width > 32768 || height > 32768)
         return fail(VR_ERR_INVALID, "vr_resize: image size out of range");
     VR_CUDA(cudaSetDevice(c->device));
+    { const int rc = drain_in_flight(c); if (rc != VR_OK) return rc; }      // frames in flight read and write the old image
     float* d_new = nullptr;
     VR_CUDA(cudaMalloc(&d_new, frame_alloc_bytes(width, height)));
     VR_CUDA(cudaMemset(d_new + (size_t)width * height * 4, 0, FRAME_SYNC_BYTES));
@@ -1123,6 +1125,8 @@ int vr_owned_rows(const vr_context* c, int* rows)
 int vr_render_device(vr_context* c, float* d_rgba, int compact, void* cuda_stream, vr_render_stats* stats)
 {
     if (!c) return fail(VR_ERR_INVALID, "vr_render_device: null context");
+    if (!d_rgba && (c->slot[0].pending || c->slot[1].pending))
+        return fail(VR_ERR_INVALID, "vr_render_device: the context's own frame is in use by frames submitted with vr_render_submit");
     if (!d_rgba) { d_rgba = c->d_frame; compact = 0; }
     VR_CUDA(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
