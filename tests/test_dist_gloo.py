@@ -127,3 +127,60 @@ def test_shared_host_frame_protocol(tmp_path, world, tile_rows, H, buffers):
     name = f"volren_test_{os.getpid()}_{world}_{buffers}"
     mp.spawn(_shared_frame_worker, args=(world, name, tile_rows, H, 24, 6, out, buffers), nprocs=world, join=True)
     assert np.load(out)[0] == 1
+
+
+def _pipelined_frame_worker(rank, world, name, tile_rows, H, W, frames, out_path):
+    """bench.py's pipelined end-to-end loop on the host side: frame f is SUBMITTED (here: remembered) before frame f - 1
+    is collected (here: written), hand-shaken and released; two shared buffers."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "volume-renderer_b200", "python")]
+    from volren_b200 import dist as vdist
+    import time
+    if rank != 0:
+        for _ in range(200):
+            try:
+                sf = vdist.SharedHostFrame(name, W, H, rank, world, create=False, register_cuda=False, buffers=2)
+                break
+            except FileNotFoundError:
+                time.sleep(0.02)
+    else:
+        sf = vdist.SharedHostFrame(name, W, H, rank, world, create=True, register_cuda=False, buffers=2)
+    ok = [1]
+    tiles = (H + tile_rows - 1) // tile_rows
+    tickets = {}
+
+    def complete(g):
+        if rank == world - 1 and g == 3:
+            time.sleep(0.05)                       # a straggler
+        buf = tickets.pop(g)
+        for t in range(rank, tiles, world):        # "the copies of frame g have landed"
+            y0, y1 = t * tile_rows, min((t + 1) * tile_rows, H)
+            ys = np.arange(y0, y1, dtype=np.float32)[:, None, None]
+            buf[y0:y1] = ys * 1000.0 + g
+        sf.mark_done(g)
+        if rank == 0:
+            sf.wait_all_done(g)
+            expect = np.arange(H, dtype=np.float32)[:, None, None] * 1000.0 + g
+            if not np.array_equal(sf.buffer_of(g), np.broadcast_to(expect, (H, W, 4))):
+                ok[0] = 0
+            sf.release(g)
+
+    for f in range(1, frames + 1):
+        sf.wait_writable(f)                        # the buffer's previous frame (f - 2) has been consumed
+        tickets[f] = sf.buffer_of(f)               # vr_render_submit(buffer of frame f)
+        if f - 1 in tickets:
+            complete(f - 1)
+    complete(frames)
+    if rank == 0:
+        np.save(out_path, np.array([ok[0]]))
+        time.sleep(0.2)
+    sf.close()
+
+
+@pytest.mark.parametrize("world,tile_rows,H", [(2, 8, 70), (4, 8, 50)])
+def test_pipelined_shared_host_frames(tmp_path, world, tile_rows, H):
+    """Order of operations of bench.py's pipelined multi-GPU end-to-end loop (vr_render_submit / vr_render_wait, two
+    frames in flight, two shared host buffers): no deadlock, no frame overwritten before the consumer has released it."""
+    out = str(tmp_path / "ok.npy")
+    name = f"volren_test_pipe_{os.getpid()}_{world}"
+    mp.spawn(_pipelined_frame_worker, args=(world, name, tile_rows, H, 24, 9, out), nprocs=world, join=True)
+    assert np.load(out)[0] == 1
