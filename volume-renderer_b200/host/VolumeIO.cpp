@@ -1,11 +1,17 @@
 // VolumeIO.cpp -- see VolumeIO.h.
 #include "VolumeIO.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <new>
 #include <sstream>
 
 #include <fcntl.h>
@@ -142,6 +148,11 @@ public:
         avail_ -= nbits;
         return v;
     }
+    // the accumulator for a hot loop that keeps it in a register: after fill(), the caller shifts `nbits` out of the
+    // returned word itself and reports what it consumed (the decoder's output pointer is a byte pointer and may alias
+    // this object as far as the compiler knows, so member updates per field would go through memory)
+    inline uint64_t peek() const { return acc_; }
+    inline void consumed(uint64_t acc_after, unsigned nbits) { acc_ = acc_after; avail_ -= nbits; }
 private:
     inline void refill()
     {
@@ -170,26 +181,69 @@ private:
     unsigned avail_ = 0;
 };
 
-// undo the channel de-interleave: the stream stores all bytes of channel 0, then channel 1 ...
-void weaveChannels(std::vector<uint8_t>& data, uint32_t channels, uint64_t block)
+// `count` predicted values of constant field width W (2..8): value += field - bias + (h[0] - h[-1]), wrapped to a byte.
+// The width is a template parameter so that every shift has an immediate count and the per-fill group unrolls; the
+// accumulator lives in a register (see BitSource::peek).  Returns the running value.
+template <unsigned W>
+inline int decodePredictedRun(BitSource& bits, const uint8_t* h, uint8_t* w, uint32_t count, int value)
 {
-    if (channels <= 1) return;
-    const uint64_t total = data.size();
+    constexpr unsigned PER_FILL = 56 / W;             // fields guaranteed after one fill()
+    constexpr int BIAS = (int)((1u << W) >> 1);
+    while (count >= PER_FILL) {
+        bits.fill();
+        uint64_t acc = bits.peek();
+#pragma GCC unroll 28
+        for (unsigned j = 0; j < PER_FILL; ++j) {
+            const int delta = (int)(uint32_t)(acc >> (64 - W)) - BIAS + (int)h[j] - (int)h[(std::ptrdiff_t)j - 1];
+            acc <<= W;
+            value = (value + delta) & 0xff;
+            w[j] = (uint8_t)value;
+        }
+        bits.consumed(acc, PER_FILL * W);
+        h += PER_FILL; w += PER_FILL; count -= PER_FILL;
+    }
+    if (count) {
+        bits.fill();
+        uint64_t acc = bits.peek();
+        for (uint32_t j = 0; j < count; ++j) {
+            const int delta = (int)(uint32_t)(acc >> (64 - W)) - BIAS + (int)h[j] - (int)h[(std::ptrdiff_t)j - 1];
+            acc <<= W;
+            value = (value + delta) & 0xff;
+            w[j] = (uint8_t)value;
+        }
+        bits.consumed(acc, count * W);
+    }
+    return value;
+}
+
+// undo the channel de-interleave: the stream stores all bytes of channel 0, then channel 1 ... (per `block` * channels
+// bytes when the file is block-interleaved, else over the whole payload).  Reads the planar bytes, writes the woven ones:
+// one pass, no temporary; 16-bit volumes (two byte planes) are zipped 16 bytes at a time.
+void weaveChannels(const uint8_t* planar, uint64_t total, uint32_t channels, uint64_t block, uint8_t* woven)
+{
     const uint64_t span = block ? (uint64_t)channels * block : total;
-    std::vector<uint8_t> tmp;
     for (uint64_t base = 0; base < total; base += span) {
         const uint64_t len = (total - base < span) ? total - base : span;
-        tmp.assign(data.begin() + (std::ptrdiff_t)base, data.begin() + (std::ptrdiff_t)(base + len));
-        uint8_t* d = data.data() + base;
+        const uint8_t* src = planar + base;
+        uint8_t* d = woven + base;
         if (channels == 2 && (len & 1) == 0) {
-            // 16-bit volumes: the two byte planes of the block, zipped
-            const uint8_t* lo = tmp.data();
-            const uint8_t* hi = tmp.data() + len / 2;
-            for (uint64_t j = 0; j < len / 2; ++j) { d[2 * j] = lo[j]; d[2 * j + 1] = hi[j]; }
+            const uint8_t* lo = src;
+            const uint8_t* hi = src + len / 2;
+            const uint64_t half = len / 2;
+            uint64_t j = 0;
+#if defined(__SSE2__)
+            for (; j + 16 <= half; j += 16) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(lo + j));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(hi + j));
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(d + 2 * j), _mm_unpacklo_epi8(a, b));
+                _mm_storeu_si128(reinterpret_cast<__m128i*>(d + 2 * j + 16), _mm_unpackhi_epi8(a, b));
+            }
+#endif
+            for (; j < half; ++j) { d[2 * j] = lo[j]; d[2 * j + 1] = hi[j]; }
         } else {
-            uint64_t src = 0;
+            uint64_t s = 0;
             for (uint32_t c = 0; c < channels; ++c)
-                for (uint64_t j = c; j < len; j += channels) d[j] = tmp[src++];
+                for (uint64_t j = c; j < len; j += channels) d[j] = src[s++];
         }
         if (span == total) break;
     }
@@ -205,9 +259,12 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
     BitSource bits(chunk, size);
     const uint32_t channels = bits.take(2) + 1;     // "skip"
     const uint32_t row = bits.take(16) + 1;         // "strip": predictor distance
+    // planar bytes first (channel 0, then channel 1 ...), in a buffer that is NOT zero-filled first (the decoder writes
+    // every byte it later reads; a std::vector would touch all of it twice)
     uint64_t cap = size * 2 + 4096;
-    out.resize(cap);
-    uint8_t* o = out.data();
+    std::unique_ptr<uint8_t[]> planar(new (std::nothrow) uint8_t[cap]);
+    if (!planar) { error = "DDS stream: out of memory"; return false; }
+    uint8_t* o = planar.get();
     uint64_t n = 0;
     int value = 0;
     for (;;) {
@@ -220,9 +277,13 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
         const unsigned width = code ? code + 1 : 0;
         const int bias = (int)((1u << width) >> 1);
         if (n + run > cap) {
-            cap = cap * 2 + run;
-            out.resize(cap);
-            o = out.data();
+            const uint64_t grown = cap * 2 + run;
+            std::unique_ptr<uint8_t[]> bigger(new (std::nothrow) uint8_t[grown]);
+            if (!bigger) { error = "DDS stream: out of memory"; return false; }
+            std::memcpy(bigger.get(), planar.get(), n);
+            planar.swap(bigger);
+            cap = grown;
+            o = planar.get();
         }
         uint32_t k = 0;
         // values that have no predictor yet (or never: row == 1)
@@ -239,24 +300,28 @@ bool ddsDecode(const uint8_t* chunk, uint64_t size, uint64_t block, std::vector<
                     o[n++] = (uint8_t)value;
                 }
             } else {
-                const unsigned per_fill = 56 / width;             // fields guaranteed after one fill()
-                while (k < run) {
-                    bits.fill();
-                    const uint32_t m = (run - k < per_fill) ? run - k : per_fill;
-                    for (uint32_t j = 0; j < m; ++j, ++h) {
-                        const int delta = (int)bits.takeUnchecked(width) - bias + (int)h[0] - (int)h[-1];
-                        value = (value + delta) & 0xff;           // wrap into 0..255
-                        o[n++] = (uint8_t)value;
-                    }
-                    k += m;
+                const uint32_t count = run - k;
+                uint8_t* w = o + n;
+                switch (width) {
+                    case 2: value = decodePredictedRun<2>(bits, h, w, count, value); break;
+                    case 3: value = decodePredictedRun<3>(bits, h, w, count, value); break;
+                    case 4: value = decodePredictedRun<4>(bits, h, w, count, value); break;
+                    case 5: value = decodePredictedRun<5>(bits, h, w, count, value); break;
+                    case 6: value = decodePredictedRun<6>(bits, h, w, count, value); break;
+                    case 7: value = decodePredictedRun<7>(bits, h, w, count, value); break;
+                    default: value = decodePredictedRun<8>(bits, h, w, count, value); break;
                 }
+                n += count;
             }
         }
     }
     // a stream without its end marker decodes zero padding until a zero count turns up: detect it here
     if (bits.exhausted()) { error = "DDS stream: missing end-of-stream marker"; return false; }
+    out.clear();
+    out.reserve(n + 1);                             // + 1: the PVM parser appends a terminator without reallocating
     out.resize(n);
-    weaveChannels(out, channels, block);
+    if (channels > 1) weaveChannels(planar.get(), n, channels, block, out.data());
+    else if (n) std::memcpy(out.data(), planar.get(), n);
     return true;
 }
 
@@ -355,7 +420,12 @@ bool pvmDecode(const uint8_t* file, uint64_t bytes, PvmVolume& out, std::string&
     }
     if (q != end) { error = "PVM: trailing bytes after payload"; return false; }
     out.width = dims[0]; out.height = dims[1]; out.depth = dims[2]; out.components = comps;
-    out.payload.assign(reinterpret_cast<const uint8_t*>(p), reinterpret_cast<const uint8_t*>(p) + vol);
+    // the payload is `vol` bytes in the middle of `body`: move them to the front in place and hand the buffer over
+    // (a copy into a fresh vector costs as much as the page faults of another width*height*depth*components bytes)
+    const size_t header = (size_t)(p - base);
+    if (header) std::memmove(body.data(), body.data() + header, (size_t)vol);
+    body.resize((size_t)vol);
+    out.payload = std::move(body);
     return true;
 }
 
