@@ -82,6 +82,41 @@ def assemble_reference(gathered: torch.Tensor, height: int, tile_rows: int) -> t
     return gathered[rank, local]
 
 
+def _interleave_over_numa_nodes(addr: int, nbytes: int) -> bool:
+    """Best effort, before the pages of a shared host frame are first touched: spread them round-robin over the NUMA
+    nodes (mbind, MPOL_INTERLEAVE; the policy of a tmpfs mapping is shared by every process that maps it).  Left alone,
+    the whole frame lands on the node of whichever process touches it first and half of the GPUs of a two-socket box
+    write their tiles across the socket link, all in one direction.  Returns False when there is
+    one node, or the call is not permitted (containers often filter it) -- nothing else changes then."""
+    try:
+        with open("/sys/devices/system/node/online") as f:
+            spec = f.read().strip()
+        nodes = []
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            nodes.extend(range(int(lo), int(hi or lo) + 1))
+        if len(nodes) < 2:
+            return False
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        page = os.sysconf("SC_PAGE_SIZE")
+        start = addr & ~(page - 1)
+        length = (addr + nbytes) - start
+        mask = 0
+        for n in nodes:
+            mask |= 1 << n
+        words = (max(nodes) // 64) + 1
+        arr = (ctypes.c_ulong * words)(*[(mask >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(words)])
+        SYS_mbind, MPOL_INTERLEAVE = 237, 3                      # x86-64
+        if os.uname().machine != "x86_64":
+            return False
+        rc = libc.syscall(SYS_mbind, ctypes.c_void_p(start), ctypes.c_ulong(length), MPOL_INTERLEAVE, arr,
+                          ctypes.c_ulong(words * 64 + 1), 0)
+        return rc == 0
+    except Exception:
+        return False
+
+
 class SharedHostFrame:
     """`buffers` W x H RGBA32F frames in POSIX shared memory, mapped by every rank process (one process per
     GPU) and page-locked in each with cudaHostRegister, so that every rank copies its own row tiles
@@ -126,6 +161,8 @@ class SharedHostFrame:
         if create:
             self.done[:] = 0
             self.released[:] = 0
+        if create:
+            self.numa_interleaved = _interleave_over_numa_nodes(self.frames.ctypes.data, buffers * width * height * 16)
         self.registered = False
         if register_cuda:
             rc = torch.cuda.cudart().cudaHostRegister(self.frames.ctypes.data, buffers * width * height * 16, 0)
