@@ -217,6 +217,27 @@ def test_headless_example_compiles_against_the_host_mirror(tmp_path):
     assert run.returncode == 2 and "usage:" in run.stderr
 
 
+def test_c_example_compiles_against_the_c_abi(tmp_path):
+    """examples/pipelined_frames.c: the drop-in boundary is a C ABI -- the header must compile as plain C11 (no C++
+    constructs), and the pipelined entry points (vr_render_submit / vr_render_wait) must link.  Without a GPU the
+    program fails loudly on its first compute call: status 1 and the library's error text, never a silent CPU path."""
+    import subprocess
+    import volren_b200 as vb
+    root = vb.REPO_ROOT
+    exe = str(tmp_path / "pipelined_frames")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "pipelined_frames.c"), "-L" + vb.LIB_DIR, "-lvolren_b200",
+           "-Wl,-rpath," + vb.LIB_DIR, "-lm", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    run = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert run.returncode == 2 and "usage:" in run.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=120)
+        assert run.returncode == 1 and "vr_create" in run.stderr
+
+
 @pytest.mark.parametrize("w,h,kind", [(64, 48, "smooth"), (131, 67, "smooth"), (17, 9, "noise"), (1, 1, "noise"), (250, 131, "noise")])
 def test_jpg_writer_decodes_with_independent_decoders(tmp_path, w, h, kind):
     """saveImage(".jpg") (RendererCore.cpp:175-176: stb quality 100): baseline JFIF, 4:4:4, unit quantiser,
