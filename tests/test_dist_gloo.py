@@ -184,3 +184,18 @@ def test_pipelined_shared_host_frames(tmp_path, world, tile_rows, H):
     name = f"volren_test_pipe_{os.getpid()}_{world}"
     mp.spawn(_pipelined_frame_worker, args=(world, name, tile_rows, H, 24, 9, out), nprocs=world, join=True)
     assert np.load(out)[0] == 1
+
+
+def test_numa_interleave_is_best_effort(tmp_path):
+    """The shared host frame asks for its pages to be interleaved over the NUMA nodes before first touch; on a
+    single-node machine or where mbind is filtered it reports False and the frame works all the same."""
+    sys.path[:0] = [os.path.join(ROOT, "volume-renderer_b200", "python")]
+    from volren_b200 import dist as vdist
+    sf = vdist.SharedHostFrame(f"volren_test_numa_{os.getpid()}", 32, 16, 0, 1, create=True, register_cuda=False, buffers=2)
+    try:
+        assert sf.numa_interleaved in (True, False)
+        sf.frames[:] = 3.0
+        assert float(sf.buffer_of(1).sum()) == 3.0 * 32 * 16 * 4
+    finally:
+        sf.close()
+
